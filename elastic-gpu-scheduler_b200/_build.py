@@ -1,0 +1,55 @@
+"""In-tree builds: libegs.so (CUDA, sm_100a) and libegs_synth.so (plain C harness helper)."""
+from __future__ import annotations
+
+import glob
+import os
+import shutil
+import subprocess
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIBDIR = os.path.join(PKG, "lib")
+LIBEGS = os.path.join(LIBDIR, "libegs.so")
+LIBSYNTH = os.path.join(LIBDIR, "libegs_synth.so")
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def _stale(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found: libegs cannot be built")
+    return p
+
+
+def build_libegs(force: bool = False, verbose: bool = False) -> str:
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                  [os.path.join(ROOT, "include", "egs.h")])
+    if force or _stale(LIBEGS, srcs):
+        os.makedirs(LIBDIR, exist_ok=True)
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+              ["-o", LIBEGS, os.path.join(CSRC, "egs_api.cu"), "-lnccl"]
+        subprocess.check_call(cmd)
+    return LIBEGS
+
+
+def build_synth(force: bool = False) -> str:
+    src = os.path.join(CSRC, "egs_synth.c")
+    if force or _stale(LIBSYNTH, [src]):
+        os.makedirs(LIBDIR, exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-std=c11", "-fPIC", "-shared", "-o", LIBSYNTH, src])
+    return LIBSYNTH
+
+
+def build_all(force: bool = False) -> None:
+    build_synth(force)
+    build_libegs(force)

@@ -1,0 +1,220 @@
+// egs_device.cuh -- device-side GPU/GPUs arithmetic of the reference's L0 layer
+// (pkg/scheduler/{gpu,rater}.go) on the int32 SoA rows.  Pure integer work.
+//
+// A node's row is free_core[8], free_mem[8]; GPUs a node does not have hold
+// EGS_PAD in BOTH arrays.  EGS_PAD = INT32_MIN fails every CanAllocate test
+// (requests are >= -1, gpu.go:51-56) and is skipped by the Rate min/max scan,
+// so no per-node gpu_count has to be read on the hot path.
+#pragma once
+#include <stdint.h>
+#include "../../include/egs.h"
+
+#define EGS_PAD INT32_MIN
+#define EGS_G EGS_MAX_GPUS
+#define EGS_C EGS_MAX_CONTAINERS
+
+// option-cache entry states (node.go:19 `allocated map[string]*GPUOption`)
+#define OPT_ABSENT 0  // no entry: the next filter Trades this node
+#define OPT_CACHED 1  // entry present: reused verbatim, even if stale (node.go:64-66)
+#define OPT_UNFIT  2  // memo: Trade failed on the CURRENT rows (cleared whenever the rows change);
+                      // the reference re-Trades such nodes every time with the same outcome
+
+// GPURequest (allocate.go:20) for one pod, by value in kernel params / shared memory.
+struct Req {
+  int C;
+  int core[EGS_C];
+  int mem[EGS_C];
+  int cnt[EGS_C];
+};
+
+__host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
+  uint64_t z = x + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t fit_term(uint32_t node) { return mix64(2ull * node + 1ull); }
+__host__ __device__ __forceinline__ uint64_t score_term(uint32_t node, int32_t score) {
+  return mix64((((uint64_t)node << 32) | (uint32_t)score) ^ 0xA5A5A5A5A5A5A5A5ull);
+}
+// candidate ordering: higher score first, then lower node id ("first max in list order").
+// Scores are >= 0 (rater.go:49-50 with operands >= 0), so key 0 means "no candidate".
+__host__ __device__ __forceinline__ uint64_t cand_key(int32_t score, uint32_t node) {
+  return ((uint64_t)(uint32_t)score << 32) | (uint64_t)(0xFFFFFFFFu - node);
+}
+__host__ __device__ __forceinline__ uint32_t key_node(uint64_t key) { return 0xFFFFFFFFu - (uint32_t)key; }
+__host__ __device__ __forceinline__ int32_t key_score(uint64_t key) { return (int32_t)(key >> 32); }
+
+// 2 x 16-byte read-only loads per array: one node's row (32 B core + 32 B mem).
+__device__ __forceinline__ void load_row(const int32_t *__restrict__ core, const int32_t *__restrict__ mem,
+                                         size_t node, int (&c)[EGS_G], int (&m)[EGS_G]) {
+  const int4 *pc = reinterpret_cast<const int4 *>(core + node * EGS_G);
+  const int4 *pm = reinterpret_cast<const int4 *>(mem + node * EGS_G);
+  int4 c0 = __ldg(pc), c1 = __ldg(pc + 1), m0 = __ldg(pm), m1 = __ldg(pm + 1);
+  c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+  m[0] = m0.x; m[1] = m0.y; m[2] = m0.z; m[3] = m0.w; m[4] = m1.x; m[5] = m1.y; m[6] = m1.z; m[7] = m1.w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast Trade: one container, fractional unit (GPUCount == 0; covers the -1 sentinel too).
+// gpu.go:110-122 tries GPU 0..G-1; the leaf keeps the option unless best > score (gpu.go:85),
+// so the LAST maximal GPU wins.  Binpack.Rate (rater.go:18-51) needs min/max of the rows after
+// the Add: tracked as top-2 so "all rows except g" is O(1) per option.
+// Returns true when some GPU fits; score / gpu index by reference.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool trade_single(const int (&c)[EGS_G], const int (&m)[EGS_G], int rc, int rm,
+                                             int policy, int &score, int &gidx) {
+  int cmin1 = INT32_MAX, cmin2 = INT32_MAX, cmax1 = INT32_MIN, cmax2 = INT32_MIN;
+  int mmin1 = INT32_MAX, mmin2 = INT32_MAX, mmax1 = INT32_MIN, mmax2 = INT32_MIN;
+  if (policy == EGS_BINPACK) {
+#pragma unroll
+    for (int g = 0; g < EGS_G; g++) {
+      bool pad = c[g] == EGS_PAD;
+      int cv = pad ? INT32_MAX : c[g], mv = pad ? INT32_MAX : m[g];
+      cmin2 = min(cmin2, max(cmin1, cv)); cmin1 = min(cmin1, cv);
+      mmin2 = min(mmin2, max(mmin1, mv)); mmin1 = min(mmin1, mv);
+      // EGS_PAD == INT32_MIN never raises a max
+      cmax2 = max(cmax2, min(cmax1, c[g])); cmax1 = max(cmax1, c[g]);
+      int mg = pad ? INT32_MIN : m[g];
+      mmax2 = max(mmax2, min(mmax1, mg)); mmax1 = max(mmax1, mg);
+    }
+  }
+  bool found = false;
+  int best = 0, bi = 0;
+#pragma unroll
+  for (int g = 0; g < EGS_G; g++) {
+    bool ok = (c[g] >= rc) && (m[g] >= rm);  // CanAllocate gpu.go:55; PAD rows fail (rc >= -1)
+    int s = 0;
+    if (policy == EGS_BINPACK) {
+      int nc = c[g] - rc, nm = m[g] - rm;     // GPU.Add gpu.go:36-37
+      int cmn = min(c[g] == cmin1 ? cmin2 : cmin1, nc), cmx = max(c[g] == cmax1 ? cmax2 : cmax1, nc);
+      int mmn = min(m[g] == mmin1 ? mmin2 : mmin1, nm), mmx = max(m[g] == mmax1 ? mmax2 : mmax1, nm);
+      int range = (mmx + cmx - mmn - cmn) / 2;  // rater.go:49
+      s = range / 2 * 100;                      // rater.go:50, gpuCount == 1
+    }
+    if (ok && !(best > s)) { best = s; bi = g; found = true; }  // gpu.go:85
+  }
+  score = best; gidx = bi;
+  return found;
+}
+
+// ---------------------------------------------------------------------------------------------
+// General Trade: up to EGS_C containers, whole-GPU units, sentinel units.  Depth-first over
+// the containers exactly as gpu.go:72-123.  Cold path: rows live in local memory.
+// ---------------------------------------------------------------------------------------------
+struct TradeCtx {
+  int c[EGS_G], m[EGS_G];
+  int mem_total, policy;
+  const Req *r;
+  uint32_t masks;       // 4 x u8: GPUs chosen per container on the current DFS path
+  int best;
+  uint32_t best_masks;
+  bool found;
+};
+
+__device__ __noinline__ void trade_leaf(TradeCtx &t) {  // gpu.go:73-93
+  int s = 0;
+  if (t.policy == EGS_BINPACK) {
+    // rateIndexes: containers holding exactly one GPU (gpu.go:76-83); k = distinct GPUs (rater.go:19-30)
+    uint32_t used = 0;
+#pragma unroll 1
+    for (int i = 0; i < t.r->C; i++) {
+      uint32_t mk = (t.masks >> (8 * i)) & 0xFFu;
+      if (__popc(mk) == 1) used |= mk;
+    }
+    int k = __popc(used);
+    int cmin = INT32_MAX, cmax = INT32_MIN, mmin = INT32_MAX, mmax = INT32_MIN;
+#pragma unroll 1
+    for (int g = 0; g < EGS_G; g++) {
+      if (t.c[g] == EGS_PAD) continue;
+      cmin = min(cmin, t.c[g]); cmax = max(cmax, t.c[g]);
+      mmin = min(mmin, t.m[g]); mmax = max(mmax, t.m[g]);
+    }
+    int range = (mmax + cmax - mmin - cmin) / 2;
+    s = range / (k + 1) * 100;
+  }
+  t.found = true;
+  if (t.best > s) return;  // gpu.go:85
+  t.best = s;
+  t.best_masks = t.masks;
+}
+
+template <int CI>
+__device__ __noinline__ void trade_dfs(TradeCtx &t) {
+  if (CI == t.r->C) { trade_leaf(t); return; }
+  const int rc = t.r->core[CI], rm = t.r->mem[CI], cnt = t.r->cnt[CI];
+  const uint32_t keep = t.masks & ~(0xFFu << (8 * CI));
+  if (cnt > 0) {  // gpu.go:95-109 with GetFreeGPUs gpu.go:193-202 on the mutated rows
+    uint32_t fm = 0; int nf = 0;
+#pragma unroll 1
+    for (int g = 0; g < EGS_G; g++)
+      if (nf < cnt && t.c[g] == EGS_CORE_PER_GPU && t.m[g] == t.mem_total) { fm |= 1u << g; nf++; }
+    if (nf < cnt) return;
+#pragma unroll 1
+    for (int g = 0; g < EGS_G; g++) if ((fm >> g) & 1u) { t.c[g] = 0; t.m[g] = 0; }          // Add gpu.go:32-34
+    t.masks = keep | (fm << (8 * CI));
+    trade_dfs<CI + 1>(t);
+#pragma unroll 1
+    for (int g = 0; g < EGS_G; g++) if ((fm >> g) & 1u) { t.c[g] = EGS_CORE_PER_GPU; t.m[g] = t.mem_total; }  // Sub gpu.go:42-44
+    t.masks = keep;
+    return;
+  }
+#pragma unroll 1
+  for (int g = 0; g < EGS_G; g++) {  // gpu.go:110-122
+    if (!(t.c[g] >= rc && t.m[g] >= rm)) continue;
+    t.c[g] -= rc; t.m[g] -= rm;
+    t.masks = keep | ((1u << g) << (8 * CI));
+    trade_dfs<CI + 1>(t);
+    t.c[g] += rc; t.m[g] += rm;
+  }
+  t.masks = keep;
+}
+template <>
+__device__ __noinline__ void trade_dfs<EGS_C>(TradeCtx &t) { trade_leaf(t); }
+
+__device__ __forceinline__ bool trade_general(const int (&c)[EGS_G], const int (&m)[EGS_G], int mem_total,
+                                              const Req &r, int policy, int &score, uint32_t &masks) {
+  TradeCtx t;
+#pragma unroll
+  for (int g = 0; g < EGS_G; g++) { t.c[g] = c[g]; t.m[g] = m[g]; }
+  t.mem_total = mem_total; t.policy = policy; t.r = &r; t.masks = 0; t.best = 0; t.best_masks = 0; t.found = false;
+  trade_dfs<0>(t);
+  score = t.best; masks = t.best_masks;
+  return t.found;
+}
+
+// One container, fractional: the shape every BASELINE config except config 3 uses.
+__device__ __forceinline__ bool req_is_single(const Req &r) { return r.C == 1 && r.cnt[0] == 0; }
+
+// Trade dispatch.  `masks` packs one u8 GPU mask per container.
+__device__ __forceinline__ bool trade_any(const int (&c)[EGS_G], const int (&m)[EGS_G], int mem_total,
+                                          const Req &r, bool single, int policy, int &score, uint32_t &masks) {
+  if (single) {
+    int g;
+    bool ok = trade_single(c, m, r.core[0], r.mem[0], policy, score, g);
+    masks = 1u << g;
+    return ok;
+  }
+  return trade_general(c, m, mem_total, r, policy, score, masks);
+}
+
+// GPUs.Transact gpu.go:153-175 on the node's rows in global memory (one thread).
+// Returns true on success; on failure the Adds already made stay (no rollback).
+__device__ __forceinline__ bool transact_row(int32_t *core, int32_t *mem, int mem_total, const Req &r,
+                                             uint32_t masks) {
+  for (int i = 0; i < r.C; i++) {
+    uint32_t mk = (masks >> (8 * i)) & 0xFFu;
+    if (r.cnt[i] > 0) {
+      for (int g = 0; g < EGS_G; g++) {
+        if (!((mk >> g) & 1u)) continue;
+        if (!(core[g] == EGS_CORE_PER_GPU && mem[g] == mem_total)) return false;
+        core[g] = 0; mem[g] = 0;
+      }
+    } else if (mk) {
+      int g = __ffs(mk) - 1;
+      if (!(core[g] >= r.core[i] && mem[g] >= r.mem[i])) return false;
+      core[g] -= r.core[i]; mem[g] -= r.mem[i];
+    }
+  }
+  return true;
+}
