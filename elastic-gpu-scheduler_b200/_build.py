@@ -37,7 +37,7 @@ def build_libegs(force: bool = False, verbose: bool = False) -> str:
     if force or _stale(LIBEGS, srcs):
         os.makedirs(LIBDIR, exist_ok=True)
         cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-              ["-o", LIBEGS, os.path.join(CSRC, "egs_api.cu"), "-lnccl"]
+              ["-o", LIBEGS, os.path.join(CSRC, "egs_api.cu"), "-ldl"]
         subprocess.check_call(cmd)
     return LIBEGS
 

@@ -23,10 +23,11 @@ EGS_PAD = -(1 << 31)
 SYMBOLS = [
     "egs_create", "egs_destroy", "egs_last_error", "egs_status_string", "egs_unit_from_requests",
     "egs_node_set_allocatable", "egs_node_set", "egs_state_load", "egs_state_load_bulk", "egs_state_dump",
+    "egs_state_snapshot", "egs_state_restore",
     "egs_filter", "egs_score", "egs_bind", "egs_option_peek", "egs_pod_apply", "egs_pod_cancel",
     "egs_pod_known", "egs_pod_released", "egs_schedule_batch", "egs_schedule_batch_device",
     "egs_shard_set", "egs_comm_unique_id", "egs_comm_init", "egs_profile_evaluate", "egs_profile_get",
-    "egs_profile_reset", "egs_mix64",
+    "egs_profile_reset", "egs_get_stream", "egs_rounds_stats", "egs_mix64",
 ]
 
 
@@ -63,6 +64,8 @@ def load(build: bool = True):
     L.egs_state_load.argtypes = [vp, i32, vp, vp]
     L.egs_state_load_bulk.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.egs_state_dump.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.egs_state_snapshot.argtypes = [vp]
+    L.egs_state_restore.argtypes = [vp]
     L.egs_filter.argtypes = [vp, i32, vp, i32, vp, vp]
     L.egs_score.argtypes = [vp, i32, vp, i32, vp, vp]
     L.egs_bind.argtypes = [vp, i32, i32, vp, u64, vp]
@@ -79,6 +82,8 @@ def load(build: bool = True):
     L.egs_profile_evaluate.argtypes = [vp, i32, vp, i32, i32, C.POINTER(C.c_float)]
     L.egs_profile_get.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(C.c_double)]
     L.egs_profile_reset.argtypes = [vp, i32]
+    L.egs_rounds_stats.argtypes = [vp, vp]
+    L.egs_get_stream.argtypes = [vp, C.POINTER(vp)]
     L.egs_mix64.argtypes = [u64]; L.egs_mix64.restype = u64
     _lib = L
     return L
@@ -155,6 +160,12 @@ class Egs:
         gc = np.zeros(n, np.int32); mt = np.zeros(n, np.int32)
         self._ck(self.L.egs_state_dump(self.h, node0, n, _p(core), _p(mem), _p(gc), _p(mt)), "egs_state_dump")
         return core, mem, gc, mt
+
+    def snapshot(self):
+        self._ck(self.L.egs_state_snapshot(self.h), "egs_state_snapshot")
+
+    def restore(self):
+        self._ck(self.L.egs_state_restore(self.h), "egs_state_restore")
 
     def rows(self, node: int):
         core, mem, gc, _ = self.state_dump(node, 1)
@@ -235,8 +246,20 @@ class Egs:
         self._ck(self.L.egs_shard_set(self.h, rank, world), "egs_shard_set")
 
     def comm_init(self, uid_bytes: bytes):
+        _one_nccl()
         buf = (C.c_uint8 * 128).from_buffer_copy(uid_bytes)
         self._ck(self.L.egs_comm_init(self.h, buf), "egs_comm_init")
+
+    def rounds_stats(self):
+        out = np.zeros(8, np.int64)
+        self._ck(self.L.egs_rounds_stats(self.h, _p(out)), "egs_rounds_stats")
+        keys = ["rounds", "pods", "tracked", "stop_limit", "stop_shape", "stop_tracked_full", "stop_list_dry"]
+        return dict(zip(keys, (int(x) for x in out[:7])))
+
+    def stream_ptr(self) -> int:
+        out = C.c_void_p()
+        self._ck(self.L.egs_get_stream(self.h, C.byref(out)), "egs_get_stream")
+        return out.value or 0
 
     def profile_evaluate(self, req, iters: int = 20, flush_l2: bool = False) -> float:
         ms = C.c_float(0)
@@ -253,7 +276,17 @@ class Egs:
         self._ck(self.L.egs_profile_reset(self.h, int(timing)), "egs_profile_reset")
 
 
+def _one_nccl():
+    """libegs resolves NCCL with dlopen("libnccl.so.2"); importing torch first makes that the
+    copy torch bundles, so the process holds a single NCCL."""
+    try:
+        import torch  # noqa: F401
+    except Exception:
+        pass
+
+
 def comm_unique_id() -> bytes:
+    _one_nccl()
     buf = (C.c_uint8 * 128)()
     st = load().egs_comm_unique_id(buf)
     if st != EGS_OK:

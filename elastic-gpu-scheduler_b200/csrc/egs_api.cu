@@ -32,6 +32,8 @@ struct egs_handle {
   int rank = 0, world = 1, lo = 0, hi = 0;
   cudaStream_t stream = nullptr;
   int32_t *d_core = nullptr, *d_mem = nullptr, *d_mem_total = nullptr;
+  int32_t *d_snap_core = nullptr, *d_snap_mem = nullptr, *d_snap_total = nullptr;
+  std::vector<int32_t> snap_gpu_count, snap_mem_total;
   std::vector<int32_t> h_gpu_count, h_mem_total;
   // option tables
   int slot_cap = 0;
@@ -212,7 +214,7 @@ extern "C" int egs_destroy(egs_handle *h) {
   cudaStreamSynchronize(h->stream);
   flush_pending(h);
   rounds_free(&h->rounds);
-  void *dev[] = {h->d_core, h->d_mem, h->d_mem_total, h->d_st, h->d_sc, h->d_al, h->d_partials, h->d_ticket,
+  void *dev[] = {h->d_core, h->d_mem, h->d_mem_total, h->d_st, h->d_sc, h->d_al, h->d_partials, h->d_ticket, h->d_snap_core, h->d_snap_mem, h->d_snap_total,
                  h->d_result, h->d_ids, h->d_fit, h->d_score, h->d_ev_fit, h->d_ev_score, h->d_ev_gpu, h->d_flush,
                  h->d_o_node, h->d_o_status, h->d_o_fit, h->d_o_alloc, h->d_o_fd, h->d_o_sd};
   for (void *p : dev) if (p) cudaFree(p);
@@ -298,9 +300,22 @@ static int load_rows(egs_handle *h, int node0, int n, int gpu_count, int mem_tot
   return EGS_OK;
 }
 
-static void drop_node_pods(egs_handle *h, int node) {
+// podsMap entries of nodes [node0, node0+n) vanish with their NodeAllocator (one pass)
+static void drop_node_pods(egs_handle *h, int node0, int n) {
+  if (h->pods_map.empty()) return;
+  if (node0 == 0 && n >= h->max_nodes) { h->pods_map.clear(); return; }
   for (auto it = h->pods_map.begin(); it != h->pods_map.end();)
-    if (it->node == node) it = h->pods_map.erase(it); else ++it;
+    if (it->node >= node0 && it->node < node0 + n) it = h->pods_map.erase(it); else ++it;
+}
+
+// wait for in-flight batches and drop their bookkeeping without applying it
+static int discard_pending(egs_handle *h) {
+  for (auto &b : h->pending) {
+    CK(h, cudaEventSynchronize(b.done));
+    cudaFreeHost(b.h_node); cudaFreeHost(b.h_status); cudaEventDestroy(b.done);
+  }
+  h->pending.clear();
+  return EGS_OK;
 }
 
 extern "C" int egs_node_set(egs_handle *h, int node_id, int gpu_count, int mem_total_per_gpu) {
@@ -308,7 +323,7 @@ extern "C" int egs_node_set(egs_handle *h, int node_id, int gpu_count, int mem_t
   Guard g(h);
   TRY(flush_pending(h));
   TRY(load_rows(h, node_id, 1, gpu_count, mem_total_per_gpu, nullptr, nullptr, true));
-  if (!h->pods_map.empty()) drop_node_pods(h, node_id);
+  drop_node_pods(h, node_id, 1);
   return EGS_OK;
 }
 
@@ -334,9 +349,10 @@ extern "C" int egs_state_load_bulk(egs_handle *h, int node0, int n, int gpu_coun
                                    const int32_t *free_core, const int32_t *free_mem) {
   if (!h) return EGS_ERR_BAD_ARG;
   Guard g(h);
+  // pending batch results only feed podsMap/podMaps; podMaps (scheduler level) survives a node reload
   TRY(flush_pending(h));
   TRY(load_rows(h, node0, n, gpu_count, mem_total, free_core, free_mem, true));
-  if (!h->pods_map.empty()) for (int i = 0; i < n; i++) drop_node_pods(h, node0 + i);
+  drop_node_pods(h, node0, n);
   return EGS_OK;
 }
 
@@ -358,6 +374,41 @@ extern "C" int egs_state_dump(egs_handle *h, int node0, int n, int32_t *free_cor
     if (gpu_count) gpu_count[i] = h->h_gpu_count[node0 + i];
     if (mem_total) mem_total[i] = h->h_mem_total[node0 + i];
   }
+  return EGS_OK;
+}
+
+extern "C" int egs_state_snapshot(egs_handle *h) {
+  if (!h) return EGS_ERR_BAD_ARG;
+  Guard g(h);
+  TRY(rounds_sync_rows(h));
+  const size_t rows = (size_t)h->n_pad * EGS_G * sizeof(int32_t);
+  if (!h->d_snap_core) {
+    CK(h, cudaMalloc(&h->d_snap_core, rows));
+    CK(h, cudaMalloc(&h->d_snap_mem, rows));
+    CK(h, cudaMalloc(&h->d_snap_total, (size_t)h->n_pad * sizeof(int32_t)));
+  }
+  CK(h, cudaMemcpyAsync(h->d_snap_core, h->d_core, rows, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_snap_mem, h->d_mem, rows, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_snap_total, h->d_mem_total, (size_t)h->n_pad * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+  h->snap_gpu_count = h->h_gpu_count; h->snap_mem_total = h->h_mem_total;
+  CK(h, cudaStreamSynchronize(h->stream));
+  return EGS_OK;
+}
+
+extern "C" int egs_state_restore(egs_handle *h) {
+  if (!h) return EGS_ERR_BAD_ARG;
+  Guard g(h);
+  if (!h->d_snap_core) return fail(h, EGS_ERR_BAD_ARG, "no snapshot");
+  TRY(discard_pending(h));
+  const size_t rows = (size_t)h->n_pad * EGS_G * sizeof(int32_t);
+  CK(h, cudaMemcpyAsync(h->d_core, h->d_snap_core, rows, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_mem, h->d_snap_mem, rows, cudaMemcpyDeviceToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_mem_total, h->d_snap_total, (size_t)h->n_pad * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
+  if (!h->shapes.empty())
+    CK(h, cudaMemsetAsync(h->d_st, OPT_ABSENT, (size_t)h->n_pad * h->shapes.size(), h->stream));
+  h->h_gpu_count = h->snap_gpu_count; h->h_mem_total = h->snap_mem_total;
+  h->pods_map.clear(); h->pod_maps.clear(); h->released.clear();
+  h->rounds.index_valid = false;
   return EGS_OK;
 }
 
@@ -689,8 +740,9 @@ extern "C" int egs_shard_set(egs_handle *h, int rank, int world) {
   if (!h || world < 1 || rank < 0 || rank >= world) return EGS_ERR_BAD_ARG;
   Guard g(h);
   h->rank = rank; h->world = world;
-  h->lo = (int)((int64_t)h->max_nodes * rank / world);
-  h->hi = (int)((int64_t)h->max_nodes * (rank + 1) / world);
+  // contiguous node ranges, boundaries on multiples of 128 (k_select reads 4-node vectors)
+  auto cut = [&](int r) { return r >= world ? h->max_nodes : (int)((int64_t)h->max_nodes * r / world) / 128 * 128; };
+  h->lo = cut(rank); h->hi = cut(rank + 1);
   h->rounds.index_valid = false;
   return EGS_OK;
 }
@@ -740,6 +792,22 @@ extern "C" int egs_profile_evaluate(egs_handle *h, int n_containers, const egs_u
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   h->k_launches[EGS_K_EVALUATE] += iters; h->k_ms[EGS_K_EVALUATE] += total;
   *out_ms_per_launch = (float)(total / iters);
+  return EGS_OK;
+}
+
+extern "C" int egs_rounds_stats(egs_handle *h, int64_t out[8]) {
+  if (!h || !out) return EGS_ERR_BAD_ARG;
+  Guard g(h);
+  const RoundsState &R = h->rounds;
+  out[0] = R.rounds; out[1] = R.pods; out[2] = R.tracked;
+  for (int i = 0; i < 4; i++) out[3 + i] = R.stops[i];
+  out[7] = 0;
+  return EGS_OK;
+}
+
+extern "C" int egs_get_stream(egs_handle *h, void **out_stream) {
+  if (!h || !out_stream) return EGS_ERR_BAD_ARG;
+  *out_stream = (void *)h->stream;
   return EGS_OK;
 }
 

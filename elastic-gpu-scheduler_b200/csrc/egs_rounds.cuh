@@ -1,14 +1,497 @@
-// egs_rounds.cuh -- EGS_MODE_ROUNDS: declarations (definitions in egs_rounds_impl.cuh,
-// included at the end of egs_api.cu once egs_handle is complete).
+// egs_rounds.cuh -- EGS_MODE_ROUNDS: the exact round-based decision loop.
+//
+// Reference semantics (node.go:61-104): a bind changes ONE node's rows and deletes ONE cache
+// entry; every other (node, shape) option -- even a stale one -- is by definition unchanged.
+// So within a stretch of pods only nodes that WON in that stretch can change.  A round is:
+//
+//   k_select  (grid, N-proportional, shardable over GPUs): per node and per shape of the
+//             round: Trade every absent option (the full-evaluate work), fold fit count and
+//             digests, keep the top-RK candidates (score desc, node asc) per shape.
+//   k_merge   (one CTA per shape): fold the per-CTA lists, gather each candidate's payload
+//             (rows + its options for all round shapes) into the shard's candidate buffer.
+//   [ncclAllGather of the candidate buffers when the node list is sharded]
+//   k_resolve (ONE warp, shared-memory resident): replays the pods one after the other:
+//             winner = max(tracked nodes' options, best untracked list head), Transact,
+//             invalidate, outputs; stops early when a list runs dry or the tracked table is
+//             full; writes the tracked nodes back.
+//
+// Option states: OPT_NEW marks an option select evaluated AHEAD of the shape's next filter.
+// It is only valid while the node's rows stay unchanged; once a pod of that shape has run
+// ("observed"), it is an ordinary cached option (OPT_CACHED).
 #pragma once
 #include <vector>
 #include "egs_kernels.cuh"
 
+#define OPT_NEW 3
+
+#define RK 32        // candidates kept per (shard, shape) per round (one per lane)
+#define RT 256       // tracked (touched) nodes per round
+#define RS 32        // shapes per round
+#define RD 8         // shards
+#define SEL_THREADS 128
+#define SEL_WARPS (SEL_THREADS / 32)
+
+struct RoundSet { int n; int slot[RS]; };
+
+struct Cand {                       // payload of one candidate node
+  unsigned long long key;           // cand_key(score, node); 0 = empty
+  int32_t rc[EGS_G], rm[EGS_G];
+  int32_t mt, pad;
+  int32_t sc[RS];
+  uint32_t al[RS];
+  uint8_t st[RS];
+};
+struct ShardBuf {                   // what one shard contributes to a round
+  int32_t len[RS], more[RS], fit[RS], pad0;
+  unsigned long long fd[RS], sd[RS];
+  Cand cand[RS][RK];
+};
+
+struct AggPart { unsigned long long fd, sd; int fit, pad; };
+
+struct TableSet {                   // all option tables of the handle
+  uint8_t *st; int32_t *sc; uint8_t *al; size_t n_pad; int n_slots;
+};
+__device__ __forceinline__ uint8_t *tb_st(const TableSet &t, int slot) { return t.st + (size_t)slot * t.n_pad; }
+__device__ __forceinline__ int32_t *tb_sc(const TableSet &t, int slot) { return t.sc + (size_t)slot * t.n_pad; }
+__device__ __forceinline__ uint8_t *tb_al(const TableSet &t, int slot) { return t.al + (size_t)slot * EGS_C * t.n_pad; }
+
+struct SelectArgs {
+  const int32_t *core, *mem, *mem_total;
+  int lo, hi, policy;               // this shard's node range
+  RoundSet set;
+  Req reqs[RS];
+  TableSet tb;
+  const uint8_t *obs_pending;       // per slot: shape observed since its OPT_NEW options were made
+  unsigned long long *cta_lists;    // [grid][RS][RK]
+  AggPart *cta_agg;                 // [grid][RS]
+};
+
+// sorted-descending list of RK keys held by lanes 0..RK-1; insert k (warp-uniform value)
+__device__ __forceinline__ void list_insert(unsigned long long &L, unsigned long long k, int lane) {
+  const unsigned gt = __ballot_sync(0xffffffffu, lane < RK && L > k);
+  const int pos = __popc(gt);
+  const unsigned long long up = __shfl_up_sync(0xffffffffu, L, 1);
+  if (lane == pos) L = k; else if (lane > pos && lane < RK) L = up;
+}
+// merge up to 32 candidate keys (one per lane, 0 = none) into the list
+__device__ __forceinline__ void list_merge(unsigned long long &L, unsigned long long cand, int lane) {
+  for (;;) {
+    const unsigned long long kth = __shfl_sync(0xffffffffu, L, RK - 1);
+    const unsigned b = __ballot_sync(0xffffffffu, cand > kth);
+    if (!b) break;
+    const int src = __ffs(b) - 1;
+    const unsigned long long k = __shfl_sync(0xffffffffu, cand, src);
+    list_insert(L, k, lane);
+    if (lane == src) cand = 0;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// k_select
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
+  __shared__ unsigned long long s_list[SEL_WARPS][RS][RK];
+  __shared__ AggPart s_agg[SEL_WARPS][RS];
+  __shared__ Req s_reqs[RS];          // kernel params are indexed dynamically: stage them in smem
+  __shared__ int s_slot[RS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * SEL_WARPS + warp, nwarps = gridDim.x * SEL_WARPS;
+  if (threadIdx.x < RS) { s_slot[threadIdx.x] = a.set.slot[threadIdx.x]; s_reqs[threadIdx.x] = a.reqs[threadIdx.x]; }
+  __syncthreads();
+  for (int s = lane; s < RS; s += 32) { s_agg[warp][s].fd = 0; s_agg[warp][s].sd = 0; s_agg[warp][s].fit = 0; }
+  for (int i = lane; i < RS * RK; i += 32) (&s_list[warp][0][0])[i] = 0;
+  __syncwarp();
+  const int n_chunks = (a.hi - a.lo + 127) / 128;
+  for (int chunk = gwarp; chunk < n_chunks; chunk += nwarps) {
+    const int base = a.lo + chunk * 128 + lane * 4;           // 4 consecutive nodes per lane
+    for (int s = 0; s < a.set.n; s++) {
+      const int slot = s_slot[s];
+      uint8_t *stp = tb_st(a.tb, slot);
+      int32_t *scp = tb_sc(a.tb, slot);
+      uint8_t *alp = tb_al(a.tb, slot);
+      const bool pending = a.obs_pending[slot] != 0;
+      const Req &r = s_reqs[s];
+      const bool single = req_is_single(r);
+      uchar4 st4 = make_uchar4(OPT_UNFIT, OPT_UNFIT, OPT_UNFIT, OPT_UNFIT);
+      int4 sc4 = make_int4(0, 0, 0, 0);
+      if (base < a.hi) {                                       // n_pad is a multiple of 1024: in-bounds vector loads
+        st4 = *reinterpret_cast<const uchar4 *>(stp + base);
+        sc4 = *reinterpret_cast<const int4 *>(scp + base);
+      }
+      uint8_t st[4] = {st4.x, st4.y, st4.z, st4.w};
+      int sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
+      bool dirty = false;
+      unsigned long long key[4], fd = 0, sd = 0;
+      int fit = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int i = base + j;
+        key[j] = 0;
+        if (i >= a.hi) continue;
+        if (st[j] == OPT_NEW && pending) { st[j] = OPT_CACHED; dirty = true; }
+        if (st[j] == OPT_ABSENT) {                             // full evaluate (gpu.go:65-129)
+          int c[EGS_G], m[EGS_G]; uint32_t masks;
+          load_row(a.core, a.mem, (size_t)i, c, m);
+          if (trade_any(c, m, a.mem_total[i], r, single, a.policy, sc[j], masks)) {
+            st[j] = OPT_NEW;
+            scp[i] = sc[j];
+            for (int k = 0; k < r.C; k++) alp[(size_t)k * a.tb.n_pad + i] = (uint8_t)(masks >> (8 * k));
+          } else {
+            st[j] = OPT_UNFIT;
+          }
+          dirty = true;
+        }
+        if (st[j] == OPT_CACHED || st[j] == OPT_NEW) {
+          key[j] = cand_key(sc[j], (uint32_t)i);
+          fit++; fd += fit_term((uint32_t)i); sd += score_term((uint32_t)i, sc[j]);
+        }
+      }
+      if (dirty && base < a.hi) *reinterpret_cast<uchar4 *>(stp + base) = make_uchar4(st[0], st[1], st[2], st[3]);
+      fit = warp_sum_i32(fit); fd = warp_sum_u64(fd); sd = warp_sum_u64(sd);
+      if (lane == 0) { s_agg[warp][s].fit += fit; s_agg[warp][s].fd += fd; s_agg[warp][s].sd += sd; }
+      // top-RK of this warp for shape s
+      unsigned long long L = lane < RK ? s_list[warp][s][lane] : 0ull;
+      bool changed = false;
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const unsigned long long kth = __shfl_sync(0xffffffffu, L, RK - 1);
+        if (__ballot_sync(0xffffffffu, key[j] > kth)) { list_merge(L, key[j], lane); changed = true; }
+      }
+      if (changed && lane < RK) s_list[warp][s][lane] = L;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // fold the warps of this CTA: warp w owns shapes s == w (mod SEL_WARPS)
+  for (int s = warp; s < a.set.n; s += SEL_WARPS) {
+    unsigned long long L = lane < RK ? s_list[0][s][lane] : 0ull;
+    for (int w = 1; w < SEL_WARPS; w++) list_merge(L, lane < RK ? s_list[w][s][lane] : 0ull, lane);
+    if (lane < RK) a.cta_lists[((size_t)blockIdx.x * RS + s) * RK + lane] = L;
+    if (lane == 0) {
+      AggPart t; t.fd = 0; t.sd = 0; t.fit = 0; t.pad = 0;
+      for (int w = 0; w < SEL_WARPS; w++) { t.fd += s_agg[w][s].fd; t.sd += s_agg[w][s].sd; t.fit += s_agg[w][s].fit; }
+      a.cta_agg[(size_t)blockIdx.x * RS + s] = t;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// k_merge: one CTA per shape of the round
+// --------------------------------------------------------------------------------------------
+struct MergeArgs {
+  const int32_t *core, *mem, *mem_total;
+  RoundSet set;
+  TableSet tb;
+  uint8_t *obs_pending;
+  const unsigned long long *cta_lists; const AggPart *cta_agg; int n_cta;
+  ShardBuf *out;
+};
+
+__global__ void __launch_bounds__(256) k_merge(MergeArgs a) {
+  __shared__ unsigned long long s_l[8][RK];
+  __shared__ AggPart s_a[8];
+  __shared__ unsigned long long s_final[RK];
+  const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long L = 0;
+  AggPart ag; ag.fd = 0; ag.sd = 0; ag.fit = 0; ag.pad = 0;
+  for (int c = warp; c < a.n_cta; c += 8) {
+    list_merge(L, lane < RK ? a.cta_lists[((size_t)c * RS + s) * RK + lane] : 0ull, lane);
+    if (lane == 0) { const AggPart p = a.cta_agg[(size_t)c * RS + s]; ag.fd += p.fd; ag.sd += p.sd; ag.fit += p.fit; }
+  }
+  if (lane < RK) s_l[warp][lane] = L;
+  if (lane == 0) s_a[warp] = ag;
+  __syncthreads();
+  if (warp == 0) {
+    L = lane < RK ? s_l[0][lane] : 0ull;
+    for (int w = 1; w < 8; w++) list_merge(L, lane < RK ? s_l[w][lane] : 0ull, lane);
+    if (lane < RK) s_final[lane] = L;
+    if (lane == 0) {
+      AggPart t = s_a[0];
+      for (int w = 1; w < 8; w++) { t.fd += s_a[w].fd; t.sd += s_a[w].sd; t.fit += s_a[w].fit; }
+      const int len = t.fit < RK ? t.fit : RK;
+      a.out->len[s] = len; a.out->more[s] = t.fit > RK; a.out->fit[s] = t.fit; a.out->fd[s] = t.fd; a.out->sd[s] = t.sd;
+      a.obs_pending[a.set.slot[s]] = 0;                        // consumed by this round's select
+    }
+  }
+  __syncthreads();
+  // payload: 16 threads per candidate, 16 candidates per pass
+  for (int k = threadIdx.x >> 4; k < RK; k += 16) {
+    const int f = threadIdx.x & 15;
+    const unsigned long long key = s_final[k];
+    Cand *cd = &a.out->cand[s][k];
+    if (key == 0) { if (f == 0) cd->key = 0; continue; }
+    const size_t node = key_node(key);
+    if (f == 0) { cd->key = key; cd->mt = a.mem_total[node]; cd->pad = 0; }
+    if (f < EGS_G) cd->rc[f] = a.core[node * EGS_G + f]; else cd->rm[f - EGS_G] = a.mem[node * EGS_G + f - EGS_G];
+    for (int s2 = f; s2 < RS; s2 += 16) {
+      uint8_t st = OPT_UNFIT; int32_t sc = 0; uint32_t al = 0;
+      if (s2 < a.set.n) {
+        const int slot = a.set.slot[s2];
+        st = tb_st(a.tb, slot)[node]; sc = tb_sc(a.tb, slot)[node];
+        const uint8_t *alp = tb_al(a.tb, slot);
+        for (int c = 0; c < EGS_C; c++) al |= (uint32_t)alp[(size_t)c * a.tb.n_pad + node] << (8 * c);
+      }
+      cd->st[s2] = st; cd->sc[s2] = sc; cd->al[s2] = al;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// k_resolve: one warp
+// --------------------------------------------------------------------------------------------
+struct ResolveArgs {
+  int32_t *core, *mem;              // write-back targets
+  int lo, hi, policy, n_shards;
+  RoundSet set;
+  Req reqs[RS];
+  TableSet tb;
+  uint8_t *obs_pending;
+  const ShardBuf *bufs;             // [n_shards]
+  const int32_t *pod_slot; int p0, p_limit;
+  PodOut out;
+  int32_t *done;                    // [0] pods resolved, [1] tracked nodes, [2] stop reason
+};
+
+#define RTW (RT / 32)
+struct ResolveSmem {                 // shape-major, padded: lanes = tracked slots OR lanes = shapes are both conflict-free
+  unsigned long long lkey[RS][RD * RK];   // untracked candidate lists (sorted, consumed entries zeroed)
+  unsigned long long tkey[RS][RT];        // cand_key of a tracked node's option when it is fit (CACHED/NEW), else 0
+  uint32_t al[RS][RT + 1];                // option.Allocated masks
+  uint8_t st[RS][RT + 4];                 // OPT_*
+  unsigned pmask[RS][RTW];                // tracked slots whose option is ABSENT: Trade at the shape's next pod
+  unsigned long long afd[RS], asd[RS];
+  int afit[RS];
+  int cur[RS][RD], len[RS][RD], more[RS][RD];
+  int observed[RS];
+  int rq_single[RS], rq_core[RS], rq_mem[RS]; uint32_t rq_cmask[RS];
+  int node[RT], mt[RT], dirty[RT];
+  int rc[RT][EGS_G], rm[RT][EGS_G];
+  Req reqs[RS];
+};
+
+__global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(smem_raw);
+  const int lane = threadIdx.x;
+  const int D = a.n_shards, ns = a.set.n, DK = D * RK;
+  // ---- prologue
+  {
+    const int s = lane;                                          // RS == 32: one shape per lane
+    int fit = 0; unsigned long long fd = 0, sd = 0;
+    for (int d = 0; d < D; d++) {
+      const ShardBuf &b = a.bufs[d];
+      S.cur[s][d] = 0; S.len[s][d] = s < ns ? b.len[s] : 0; S.more[s][d] = s < ns ? b.more[s] : 0;
+      if (s < ns) { fit += b.fit[s]; fd += b.fd[s]; sd += b.sd[s]; }
+    }
+    S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd; S.observed[s] = 0;
+    for (int w = 0; w < RTW; w++) S.pmask[s][w] = 0;
+    if (s < ns) {
+      S.reqs[s] = a.reqs[s];
+      const Req &r = a.reqs[s];
+      S.rq_single[s] = req_is_single(r); S.rq_core[s] = r.core[0]; S.rq_mem[s] = r.mem[0];
+      S.rq_cmask[s] = r.C >= 4 ? 0xFFFFFFFFu : ((1u << (8 * r.C)) - 1u);   // alloc planes >= C are never written
+    }
+  }
+  for (int s = 0; s < ns; s++)
+    for (int e = lane; e < DK; e += 32) S.lkey[s][e] = a.bufs[e / RK].cand[s][e % RK].key;
+  __syncwarp();
+  int nT = 0, done = 0, reason = 0;
+  const int my_set_slot = lane < ns ? a.set.slot[lane] : -1;
+  int myslots = -1;
+  // ---- sequential replay
+  for (int p = a.p0; p < a.p_limit; p++) {
+    const int rel = p - a.p0;
+    if ((rel & 31) == 0) myslots = (p + lane < a.p_limit) ? a.pod_slot[p + lane] : -1;   // one L2 trip per 32 pods
+    const int pslot = __shfl_sync(0xffffffffu, myslots, rel & 31);
+    const unsigned mb = __ballot_sync(0xffffffffu, my_set_slot == pslot);
+    if (!mb) { reason = 1; break; }                              // shape outside this round's set
+    const int s = __ffs(mb) - 1;
+    if (nT >= RT) { reason = 2; break; }                          // no free tracked slot for a new winner
+    // best untracked candidate per shard (lists are sorted; consumed entries are zeroed)
+    unsigned long long head = 0; bool dry = false; int hk = 0;
+    if (lane < D) {
+      int c = S.cur[s][lane];
+      const int len = S.len[s][lane];
+      while (c < len && S.lkey[s][lane * RK + c] == 0) c++;
+      S.cur[s][lane] = c;
+      if (c < len) { head = S.lkey[s][lane * RK + c]; hk = c; } else dry = S.more[s][lane] != 0;
+    }
+    if (__ballot_sync(0xffffffffu, dry)) { reason = 3; break; }   // a truncated list ran dry: next round
+    if (!S.observed[s]) {                                          // first pod of this shape in the round:
+      for (int t = lane; t < nT; t += 32) if (S.st[s][t] == OPT_NEW) S.st[s][t] = OPT_CACHED;   // NEW options are now ordinary
+      __syncwarp();
+      if (lane == 0) S.observed[s] = 1;
+      __syncwarp();
+    }
+    const int single = S.rq_single[s];
+    // tracked nodes: Trade absent options NOW (this pod's filter); best tracked option
+    unsigned long long best = 0; int best_t = -1;
+    const int nw = (nT + 31) >> 5;
+    for (int w = 0; w < nw; w++) {
+      const unsigned word = S.pmask[s][w];
+      const int t = w * 32 + lane;
+      if (word) {
+        if ((word >> lane) & 1u) {
+          int sc; uint32_t masks; bool ok;
+          if (single) { int g; ok = trade_single(S.rc[t], S.rm[t], S.rq_core[s], S.rq_mem[s], a.policy, sc, g); masks = 1u << g; }
+          else ok = trade_general(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], a.policy, sc, masks);
+          if (ok) {
+            const uint32_t nd = (uint32_t)S.node[t];
+            S.st[s][t] = OPT_CACHED; S.al[s][t] = masks; S.tkey[s][t] = cand_key(sc, nd);
+            atomicAdd(&S.afit[s], 1); atomicAdd(&S.afd[s], fit_term(nd)); atomicAdd(&S.asd[s], score_term(nd, sc));
+          } else {
+            S.st[s][t] = OPT_UNFIT;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) S.pmask[s][w] = 0;
+      }
+      const unsigned long long k = t < nT ? S.tkey[s][t] : 0ull;
+      if (k > best) { best = k; best_t = t; }
+    }
+    __syncwarp();
+    // winner = max over (tracked options, untracked list heads): two redux.sync steps on the key halves
+    const bool from_head = head > best;
+    const unsigned long long mine = from_head ? head : best;
+    const unsigned hi = (unsigned)(mine >> 32);
+    const unsigned m1 = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned m2 = __reduce_max_sync(0xffffffffu, hi == m1 ? (unsigned)mine : 0u);
+    const unsigned long long win = ((unsigned long long)m1 << 32) | m2;
+    const int fitc = S.afit[s];
+    const unsigned long long ofd = S.afd[s], osd = S.asd[s];
+    int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
+    if (win != 0) {
+      const int owner = __ffs(__ballot_sync(0xffffffffu, mine == win)) - 1;
+      int t;
+      if (__shfl_sync(0xffffffffu, (int)from_head, owner)) {
+        // an untracked node wins: it becomes tracked (payload from the candidate buffer)
+        const int k = __shfl_sync(0xffffffffu, hk, owner);
+        const Cand &cd = a.bufs[owner].cand[s][k];
+        t = nT++;
+        const uint32_t w = key_node(win);
+        if (lane < EGS_G) S.rc[t][lane] = cd.rc[lane]; else if (lane < 2 * EGS_G) S.rm[t][lane - EGS_G] = cd.rm[lane - EGS_G];
+        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = cd.mt; S.dirty[t] = 0; }
+        {
+          uint8_t st = cd.st[lane];                                // lane == shape index
+          if (st == OPT_NEW && S.observed[lane]) st = OPT_CACHED;
+          S.st[lane][t] = st; S.al[lane][t] = cd.al[lane];
+          S.tkey[lane][t] = (st == OPT_CACHED || st == OPT_NEW) ? cand_key(cd.sc[lane], w) : 0ull;
+          if (st == OPT_ABSENT) S.pmask[lane][t >> 5] |= 1u << (t & 31);
+        }
+        for (int s2 = 0; s2 < ns; s2++)                            // it leaves every untracked list
+          for (int e = lane; e < DK; e += 32) {
+            const unsigned long long q = S.lkey[s2][e];
+            if (q != 0 && key_node(q) == w) S.lkey[s2][e] = 0;
+          }
+        __syncwarp();
+      } else {
+        t = __shfl_sync(0xffffffffu, best_t, owner);
+      }
+      // Bind: NodeAllocator.Allocate (node.go:87-104) on the tracked copy
+      o_node = S.node[t];
+      const uint32_t masks = S.al[s][t] & S.rq_cmask[s];
+      const unsigned pbit = 1u << (t & 31);
+      int ok = 0;
+      if (lane == 0) {
+        S.st[s][t] = OPT_ABSENT; S.tkey[s][t] = 0; S.pmask[s][t >> 5] |= pbit;    // deferred delete, node.go:90-92
+        S.afit[s] = fitc - 1; S.afd[s] = ofd - fit_term((uint32_t)o_node); S.asd[s] = osd - score_term((uint32_t)o_node, key_score(win));
+        if (single) {                                               // GPUs.Transact gpu.go:164-171
+          const int g = __ffs(masks) - 1;
+          const int c = S.rc[t][g], m = S.rm[t][g], rc = S.rq_core[s], rm = S.rq_mem[s];
+          ok = (c >= rc && m >= rm) ? 1 : 0;
+          if (ok) { S.rc[t][g] = c - rc; S.rm[t][g] = m - rm; }
+        } else {
+          ok = transact_row(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], masks) ? 1 : 0;
+        }
+        S.dirty[t] = 1;
+      }
+      ok = __shfl_sync(0xffffffffu, ok, 0);
+      // rows changed: UNFIT memos and not-yet-observed NEW options of this node are void
+      if (lane < ns && lane != s) {
+        const uint8_t v = S.st[lane][t];
+        if (v == OPT_UNFIT) { S.st[lane][t] = OPT_ABSENT; S.pmask[lane][t >> 5] |= pbit; }
+        else if (v == OPT_NEW && !S.observed[lane]) {
+          const unsigned long long k2 = S.tkey[lane][t];
+          S.st[lane][t] = OPT_ABSENT; S.tkey[lane][t] = 0; S.pmask[lane][t >> 5] |= pbit;
+          S.afit[lane] -= 1; S.afd[lane] -= fit_term((uint32_t)o_node); S.asd[lane] -= score_term((uint32_t)o_node, key_score(k2));
+        }
+      }
+      __syncwarp();
+      o_status = ok ? EGS_OK : EGS_ERR_TRANSACT;
+      o_masks = ok ? masks : 0;
+    }
+    if (lane == 0) {
+      if (a.out.node) a.out.node[p] = o_node;
+      if (a.out.status) a.out.status[p] = o_status;
+      if (a.out.fit_count) a.out.fit_count[p] = fitc;
+      if (a.out.fit_digest) a.out.fit_digest[p] = ofd;
+      if (a.out.score_digest) a.out.score_digest[p] = osd;
+      if (a.out.alloc) *reinterpret_cast<uint32_t *>(a.out.alloc + (size_t)p * EGS_C) = o_masks;
+    }
+    done++;
+  }
+  __syncwarp();
+  // ---- epilogue: write the tracked nodes back (each shard its own nodes)
+  for (int t = 0; t < nT; t++) {
+    const int w = S.node[t];
+    if (w < a.lo || w >= a.hi) continue;
+    if (S.dirty[t]) {
+      if (lane < EGS_G) a.core[(size_t)w * EGS_G + lane] = S.rc[t][lane];
+      else if (lane < 2 * EGS_G) a.mem[(size_t)w * EGS_G + lane - EGS_G] = S.rm[t][lane - EGS_G];
+    }
+    if (lane < ns) {
+      const int slot = a.set.slot[lane];
+      const uint8_t st = S.st[lane][t];
+      tb_st(a.tb, slot)[w] = st;
+      if (st == OPT_CACHED || st == OPT_NEW) {
+        tb_sc(a.tb, slot)[w] = key_score(S.tkey[lane][t]);
+        uint8_t *alp = tb_al(a.tb, slot);
+        const uint32_t am = S.al[lane][t];
+        for (int c = 0; c < S.reqs[lane].C; c++) alp[(size_t)c * a.tb.n_pad + w] = (uint8_t)(am >> (8 * c));
+      }
+    }
+    if (S.dirty[t]) {                                            // shapes outside the round set
+      for (int slot = lane; slot < a.tb.n_slots; slot += 32) {
+        bool in_set = false;
+        for (int q = 0; q < ns; q++) in_set |= a.set.slot[q] == slot;
+        if (in_set) continue;
+        uint8_t *q = tb_st(a.tb, slot) + w;
+        if (*q == OPT_UNFIT) *q = OPT_ABSENT;
+        else if (*q == OPT_NEW) *q = a.obs_pending[slot] ? OPT_CACHED : OPT_ABSENT;
+      }
+    }
+  }
+  if (lane < ns && S.observed[lane]) a.obs_pending[a.set.slot[lane]] = 1;
+  if (lane == 0) { a.done[0] = done; a.done[1] = nT; a.done[2] = reason; }
+}
+
+// End of a ROUNDS batch: no OPT_NEW may outlive it (the other code paths know three states).
+__global__ void k_rounds_finalize(TableSet tb, uint8_t *obs_pending, int lo, int hi) {
+  const int i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  for (int slot = 0; slot < tb.n_slots; slot++) {
+    uint8_t *q = tb_st(tb, slot) + i;
+    if (*q == OPT_NEW) *q = obs_pending[slot] ? OPT_CACHED : OPT_ABSENT;
+  }
+}
+__global__ void k_clear_u8(uint8_t *p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 struct egs_handle;
 
 struct RoundsState {
-  bool index_valid = false;     // per-shape candidate index is in step with rows + option tables
-  void *comm = nullptr;         // ncclComm_t
+  bool index_valid = false;
+  void *comm = nullptr;             // ncclComm_t
+  int32_t *d_pod_slot = nullptr; int pod_cap = 0;
+  uint8_t *d_obs = nullptr; int obs_cap = 0;
+  unsigned long long *d_cta_lists = nullptr; AggPart *d_cta_agg = nullptr; int grid = 0;
+  ShardBuf *d_bufs = nullptr;       // [RD]; own shard written at index `rank`
+  int32_t *d_done = nullptr; int32_t *h_done = nullptr;
+  int64_t rounds = 0, pods = 0, tracked = 0; int64_t stops[4] = {0, 0, 0, 0};
 };
 
 static int batch_rescan(egs_handle *h, int P, const int32_t *c_off, const egs_unit *units,

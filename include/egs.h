@@ -91,6 +91,12 @@ int egs_state_load_bulk(egs_handle *h, int node0, int n, int gpu_count, int mem_
 int egs_state_dump(egs_handle *h, int node0, int n, int32_t *free_core, int32_t *free_mem,
                    int32_t *gpu_count, int32_t *mem_total);
 
+/* Device-side checkpoint of the rows, and its restore.  Restore also empties every option
+ * cache and the pod maps: the state of a freshly restarted scheduler whose node cache was
+ * rebuilt (scheduler.go:86-106).  Used by bench.py to start every step from the same cluster. */
+int egs_state_snapshot(egs_handle *h);
+int egs_state_restore(egs_handle *h);
+
 /* ---- verbs (one pod at a time; host buffers) -------------------------------- */
 
 /* Assume: for each candidate node (node_ids == NULL means 0..n-1) cache hit -> fit,
@@ -166,7 +172,7 @@ int egs_comm_init(egs_handle *h, const uint8_t id[128]);
 
 /* ---- instrumentation --------------------------------------------------------- */
 
-enum egs_kernel_id { EGS_K_EVALUATE = 0, EGS_K_PASS = 1, EGS_K_SELECT = 2, EGS_K_RESOLVE = 3, EGS_K_COUNT = 8 };
+enum egs_kernel_id { EGS_K_EVALUATE = 0, EGS_K_PASS = 1, EGS_K_SELECT = 2, EGS_K_RESOLVE = 3, EGS_K_MERGE = 4, EGS_K_COUNT = 8 };
 /* Full-evaluate kernel alone (every candidate node Traded, no cache shortcut): runs
  * `iters` launches over nodes [0,n) for one request and reports the mean launch time
  * measured with CUDA events on the launching stream.  Does not modify the option cache. */
@@ -175,6 +181,15 @@ int egs_profile_evaluate(egs_handle *h, int n_containers, const egs_unit *units,
 /* Launch counters / accumulated event time per kernel since the last reset. */
 int egs_profile_get(egs_handle *h, int kernel_id, int64_t *out_launches, double *out_ms);
 int egs_profile_reset(egs_handle *h, int enable_timing);
+
+/* Counters of the round-based loop since creation: [0] rounds, [1] pods resolved, [2] tracked
+ * nodes (sum over rounds), [3..6] rounds stopped by: pod limit, shape outside the round set,
+ * tracked table full, candidate list dry. */
+int egs_rounds_stats(egs_handle *h, int64_t out[8]);
+
+/* The CUDA stream (cudaStream_t) every kernel of this handle is launched on, so that callers
+ * can bracket work with CUDA events on the launching stream. */
+int egs_get_stream(egs_handle *h, void **out_stream);
 
 /* splitmix64 output function used by the digests */
 uint64_t egs_mix64(uint64_t x);
