@@ -2,6 +2,7 @@
 // SoA node/GPU cache.  No CPU fallback exists: every verb runs a CUDA kernel or fails.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -146,7 +147,7 @@ static Req make_req(int C, const egs_unit *u) {
   for (int i = 0; i < C; i++) { r.core[i] = u[i].core; r.mem[i] = u[i].mem; r.cnt[i] = u[i].count; }
   return r;
 }
-static bool is_single(int C, const egs_unit *u) { return C == 1 && u[0].count == 0; }
+static bool is_single(int C, const egs_unit *u) { return C == 1 && u[0].count == 0 && u[0].core >= 0 && u[0].mem >= 0; }
 
 static int flush_pending(egs_handle *h) {
   for (auto &b : h->pending) {
@@ -772,16 +773,26 @@ extern "C" int egs_profile_evaluate(egs_handle *h, int n_containers, const egs_u
   a.core = h->d_core; a.mem = h->d_mem; a.mem_total = h->d_mem_total; a.n = h->max_nodes; a.policy = h->policy;
   a.req = make_req(n_containers, units); a.fit = h->d_ev_fit; a.score = h->d_ev_score; a.gpu = h->d_ev_gpu; a.plane = np;
   const bool single = is_single(n_containers, units);
-  constexpr int ITEMS = 2;
-  const int grid = (h->max_nodes + 256 * ITEMS - 1) / (256 * ITEMS);
+  int items = 2;                                  // nodes per thread (tuning knob for experiments)
+  if (const char *ev = getenv("EGS_EVAL_ITEMS")) items = atoi(ev);
+  if (items != 1 && items != 2 && items != 4) items = 2;
+  const int grid = (h->max_nodes + 256 * items - 1) / (256 * items);
+  auto launch = [&]() {
+    if (single) {
+      if (items == 1) k_evaluate<true, 1><<<grid, 256, 0, h->stream>>>(a);
+      else if (items == 2) k_evaluate<true, 2><<<grid, 256, 0, h->stream>>>(a);
+      else k_evaluate<true, 4><<<grid, 256, 0, h->stream>>>(a);
+    } else {
+      k_evaluate<false, 1><<<(h->max_nodes + 255) / 256, 256, 0, h->stream>>>(a);
+    }
+  };
   cudaEvent_t e0, e1;
   CK(h, cudaEventCreate(&e0)); CK(h, cudaEventCreate(&e1));
   double total = 0;
   for (int it = 0; it < iters; it++) {
     if (flush_l2) CK(h, cudaMemsetAsync(h->d_flush, it & 0xff, flush_bytes, h->stream));
     CK(h, cudaEventRecord(e0, h->stream));
-    if (single) k_evaluate<true, ITEMS><<<grid, 256, 0, h->stream>>>(a);
-    else k_evaluate<false, ITEMS><<<grid, 256, 0, h->stream>>>(a);
+    launch();
     CK(h, cudaEventRecord(e1, h->stream));
     CK(h, cudaEventSynchronize(e1));
     float ms = 0;

@@ -56,46 +56,50 @@ __device__ __forceinline__ void load_row(const int32_t *__restrict__ core, const
 }
 
 // ---------------------------------------------------------------------------------------------
-// Fast Trade: one container, fractional unit (GPUCount == 0; covers the -1 sentinel too).
+// Fast Trade: one container, fractional unit with core >= 0 and mem >= 0 (GPUCount == 0).
 // gpu.go:110-122 tries GPU 0..G-1; the leaf keeps the option unless best > score (gpu.go:85),
-// so the LAST maximal GPU wins.  Binpack.Rate (rater.go:18-51) needs min/max of the rows after
-// the Add: tracked as top-2 so "all rows except g" is O(1) per option.
+// so the LAST maximal GPU wins.  Binpack.Rate (rater.go:18-51) needs min/max over all rows
+// after the Add on GPU g:
+//   * new value n = row[g] - req <= row[g], so  min' = min(min_all, n)           (no exclusion needed)
+//   * max' = max(max over rows != g, n): prefix/suffix maxima + one 3-input max
+//   * PAD (0x80000000) is the largest UNSIGNED and the smallest SIGNED value: an unsigned min
+//     and a signed max both ignore absent GPUs without any select (valid rows are >= 0).
+//   * score = Range/(1+1)*100 with Range = x/2, x >= 0  ==  (x >> 2) * 100        (rater.go:49-50)
+//   * candidates are folded as key = q*8 + g: one max keeps the last maximal GPU.
 // Returns true when some GPU fits; score / gpu index by reference.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool trade_single(const int (&c)[EGS_G], const int (&m)[EGS_G], int rc, int rm,
                                              int policy, int &score, int &gidx) {
-  int cmin1 = INT32_MAX, cmin2 = INT32_MAX, cmax1 = INT32_MIN, cmax2 = INT32_MIN;
-  int mmin1 = INT32_MAX, mmin2 = INT32_MAX, mmax1 = INT32_MIN, mmax2 = INT32_MIN;
+  int bestkey = -1;
   if (policy == EGS_BINPACK) {
+    unsigned ucmin = 0xFFFFFFFFu, ummin = 0xFFFFFFFFu;
+    int cpre[EGS_G], csuf[EGS_G], mpre[EGS_G], msuf[EGS_G];
+    cpre[0] = INT32_MIN; mpre[0] = INT32_MIN; csuf[EGS_G - 1] = INT32_MIN; msuf[EGS_G - 1] = INT32_MIN;
+#pragma unroll
+    for (int g = 0; g < EGS_G; g++) { ucmin = min(ucmin, (unsigned)c[g]); ummin = min(ummin, (unsigned)m[g]); }
+#pragma unroll
+    for (int g = 1; g < EGS_G; g++) { cpre[g] = max(cpre[g - 1], c[g - 1]); mpre[g] = max(mpre[g - 1], m[g - 1]); }
+#pragma unroll
+    for (int g = EGS_G - 2; g >= 0; g--) { csuf[g] = max(csuf[g + 1], c[g + 1]); msuf[g] = max(msuf[g + 1], m[g + 1]); }
+    const int cmin = (int)ucmin, mmin = (int)ummin;
 #pragma unroll
     for (int g = 0; g < EGS_G; g++) {
-      bool pad = c[g] == EGS_PAD;
-      int cv = pad ? INT32_MAX : c[g], mv = pad ? INT32_MAX : m[g];
-      cmin2 = min(cmin2, max(cmin1, cv)); cmin1 = min(cmin1, cv);
-      mmin2 = min(mmin2, max(mmin1, mv)); mmin1 = min(mmin1, mv);
-      // EGS_PAD == INT32_MIN never raises a max
-      cmax2 = max(cmax2, min(cmax1, c[g])); cmax1 = max(cmax1, c[g]);
-      int mg = pad ? INT32_MIN : m[g];
-      mmax2 = max(mmax2, min(mmax1, mg)); mmax1 = max(mmax1, mg);
+      const bool ok = (c[g] >= rc) && (m[g] >= rm);         // CanAllocate gpu.go:55; PAD rows fail
+      const int nc = c[g] - rc, nm = m[g] - rm;             // GPU.Add gpu.go:36-37
+      const int cmx = __vimax3_s32(cpre[g], csuf[g], nc), cmn = min(cmin, nc);
+      const int mmx = __vimax3_s32(mpre[g], msuf[g], nm), mmn = min(mmin, nm);
+      const int x = (mmx + cmx) - (mmn + cmn);
+      const int key = ok ? ((x >> 2) * 8 + g) : -1;
+      bestkey = max(bestkey, key);
     }
-  }
-  bool found = false;
-  int best = 0, bi = 0;
+    score = (bestkey >> 3) * 100;
+  } else {                                                   // Spread.Rate == 0 (rater.go:56-59): last feasible GPU
 #pragma unroll
-  for (int g = 0; g < EGS_G; g++) {
-    bool ok = (c[g] >= rc) && (m[g] >= rm);  // CanAllocate gpu.go:55; PAD rows fail (rc >= -1)
-    int s = 0;
-    if (policy == EGS_BINPACK) {
-      int nc = c[g] - rc, nm = m[g] - rm;     // GPU.Add gpu.go:36-37
-      int cmn = min(c[g] == cmin1 ? cmin2 : cmin1, nc), cmx = max(c[g] == cmax1 ? cmax2 : cmax1, nc);
-      int mmn = min(m[g] == mmin1 ? mmin2 : mmin1, nm), mmx = max(m[g] == mmax1 ? mmax2 : mmax1, nm);
-      int range = (mmx + cmx - mmn - cmn) / 2;  // rater.go:49
-      s = range / 2 * 100;                      // rater.go:50, gpuCount == 1
-    }
-    if (ok && !(best > s)) { best = s; bi = g; found = true; }  // gpu.go:85
+    for (int g = 0; g < EGS_G; g++) bestkey = ((c[g] >= rc) && (m[g] >= rm)) ? g : bestkey;
+    score = 0;
   }
-  score = best; gidx = bi;
-  return found;
+  gidx = bestkey & 7;
+  return bestkey >= 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -183,8 +187,10 @@ __device__ __forceinline__ bool trade_general(const int (&c)[EGS_G], const int (
   return t.found;
 }
 
-// One container, fractional: the shape every BASELINE config except config 3 uses.
-__device__ __forceinline__ bool req_is_single(const Req &r) { return r.C == 1 && r.cnt[0] == 0; }
+// One container, fractional, non-negative: the shape every BASELINE config except config 3 uses.
+__host__ __device__ __forceinline__ bool req_is_single(const Req &r) {
+  return r.C == 1 && r.cnt[0] == 0 && r.core[0] >= 0 && r.mem[0] >= 0;
+}
 
 // Trade dispatch.  `masks` packs one u8 GPU mask per container.
 __device__ __forceinline__ bool trade_any(const int (&c)[EGS_G], const int (&m)[EGS_G], int mem_total,

@@ -4,14 +4,16 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r01}
-python bench.py --steps 3 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
-tail -c 3000 gpurun_out/bench_${TAG}.json; tail -5 gpurun_out/bench_${TAG}.err
+timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench_${TAG}.json 2> gpurun_out/bench_${TAG}.err
+tail -c 4000 gpurun_out/bench_${TAG}.json; tail -5 gpurun_out/bench_${TAG}.err
+timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_${TAG}.json 2>> gpurun_out/bench_${TAG}.err
+tail -c 1500 gpurun_out/bench_ref_${TAG}.json
 # launch list (per-launch device time; cold-cache, serialised: compare shares)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_${TAG}.csv \
-    python bench.py --steps 1 --warmup 1 --pods 150 --no-cpu > gpurun_out/ncu_bench_${TAG}.log 2>&1
-tail -3 gpurun_out/ncu_bench_${TAG}.log | cut -c1-300
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_${TAG}.csv \
+    python bench.py --steps 1 --warmup 1 --pods 30000 --no-cpu > gpurun_out/ncu_bench_${TAG}.log 2>&1
+tail -2 gpurun_out/ncu_bench_${TAG}.log | cut -c1-300
 # full capture of the evaluate kernel (HBM-resident 4M-node launches come first in the roofline leg)
-ncu --set full --clock-control none --import-source on -k regex:k_evaluate -s 3 -c 2 -o gpurun_out/prof_evaluate_${TAG} -f \
-    python bench.py --steps 1 --warmup 0 --pods 50 --no-cpu > gpurun_out/ncu_eval_${TAG}.log 2>&1
-tail -3 gpurun_out/ncu_eval_${TAG}.log | cut -c1-300
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_evaluate -s 3 -c 2 -o gpurun_out/prof_evaluate_${TAG} -f \
+    python bench.py --steps 1 --warmup 0 --pods 2000 --no-cpu > gpurun_out/ncu_eval_${TAG}.log 2>&1
+tail -2 gpurun_out/ncu_eval_${TAG}.log | cut -c1-300
 ls -la gpurun_out | tail -12
