@@ -26,7 +26,7 @@ SYMBOLS = [
     "egs_state_snapshot", "egs_state_restore",
     "egs_filter", "egs_score", "egs_bind", "egs_option_peek", "egs_pod_apply", "egs_pod_cancel",
     "egs_pod_known", "egs_pod_released", "egs_schedule_batch", "egs_schedule_batch_device",
-    "egs_shard_set", "egs_comm_unique_id", "egs_comm_init", "egs_profile_evaluate", "egs_profile_get",
+    "egs_shard_set", "egs_shard_range", "egs_comm_unique_id", "egs_comm_init", "egs_profile_evaluate", "egs_profile_get",
     "egs_profile_reset", "egs_get_stream", "egs_rounds_stats", "egs_mix64",
 ]
 
@@ -77,6 +77,7 @@ def load(build: bool = True):
     L.egs_schedule_batch.argtypes = [vp, i32, i32, vp, vp, vp] + [vp] * 6
     L.egs_schedule_batch_device.argtypes = [vp, i32, i32, vp, vp] + [vp] * 6
     L.egs_shard_set.argtypes = [vp, i32, i32]
+    L.egs_shard_range.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.egs_comm_unique_id.argtypes = [vp]
     L.egs_comm_init.argtypes = [vp, vp]
     L.egs_profile_evaluate.argtypes = [vp, i32, vp, i32, i32, C.POINTER(C.c_float)]
@@ -283,6 +284,14 @@ def _one_nccl():
         import torch  # noqa: F401
     except Exception:
         pass
+
+
+def shard_range(max_nodes: int, rank: int, world: int):
+    lo, hi = C.c_int(0), C.c_int(0)
+    st = load().egs_shard_range(max_nodes, rank, world, C.byref(lo), C.byref(hi))
+    if st != EGS_OK:
+        raise EgsError(st, "egs_shard_range")
+    return lo.value, hi.value
 
 
 def comm_unique_id() -> bytes:

@@ -737,13 +737,19 @@ extern "C" int egs_schedule_batch_device(egs_handle *h, int mode, int n_pods, co
 }
 
 // ------------------------------------------------------------------------------- sharding
+extern "C" int egs_shard_range(int max_nodes, int rank, int world, int *lo, int *hi) {
+  if (max_nodes < 1 || world < 1 || rank < 0 || rank >= world || !lo || !hi) return EGS_ERR_BAD_ARG;
+  // contiguous node ranges, boundaries on multiples of 128 (k_select reads 4-node vectors)
+  auto cut = [&](int r) { return r >= world ? max_nodes : (int)((int64_t)max_nodes * r / world) / 128 * 128; };
+  *lo = cut(rank); *hi = cut(rank + 1);
+  return EGS_OK;
+}
+
 extern "C" int egs_shard_set(egs_handle *h, int rank, int world) {
-  if (!h || world < 1 || rank < 0 || rank >= world) return EGS_ERR_BAD_ARG;
+  if (!h || world < 1 || world > RD || rank < 0 || rank >= world) return EGS_ERR_BAD_ARG;
   Guard g(h);
   h->rank = rank; h->world = world;
-  // contiguous node ranges, boundaries on multiples of 128 (k_select reads 4-node vectors)
-  auto cut = [&](int r) { return r >= world ? h->max_nodes : (int)((int64_t)h->max_nodes * r / world) / 128 * 128; };
-  h->lo = cut(rank); h->hi = cut(rank + 1);
+  egs_shard_range(h->max_nodes, rank, world, &h->lo, &h->hi);
   h->rounds.index_valid = false;
   return EGS_OK;
 }

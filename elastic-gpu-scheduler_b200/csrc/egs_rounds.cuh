@@ -266,6 +266,7 @@ struct ResolveSmem {                 // shape-major, padded: lanes = tracked slo
   int observed[RS];
   int rq_single[RS], rq_core[RS], rq_mem[RS]; uint32_t rq_cmask[RS];
   int node[RT], mt[RT], dirty[RT];
+  unsigned long long fterm[RT];           // fit_term(node) of each tracked slot
   int rc[RT][EGS_G], rm[RT][EGS_G];
   Req reqs[RS];
 };
@@ -332,19 +333,20 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
       const unsigned word = S.pmask[s][w];
       const int t = w * 32 + lane;
       if (word) {
+        bool ok = false; int sc = 0;
         if ((word >> lane) & 1u) {
-          int sc; uint32_t masks; bool ok;
+          uint32_t masks;
           if (single) { int g; ok = trade_single(S.rc[t], S.rm[t], S.rq_core[s], S.rq_mem[s], a.policy, sc, g); masks = 1u << g; }
           else ok = trade_general(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], a.policy, sc, masks);
-          if (ok) {
-            const uint32_t nd = (uint32_t)S.node[t];
-            S.st[s][t] = OPT_CACHED; S.al[s][t] = masks; S.tkey[s][t] = cand_key(sc, nd);
-            atomicAdd(&S.afit[s], 1); atomicAdd(&S.afd[s], fit_term(nd)); atomicAdd(&S.asd[s], score_term(nd, sc));
-          } else {
-            S.st[s][t] = OPT_UNFIT;
-          }
+          if (ok) { S.st[s][t] = OPT_CACHED; S.al[s][t] = masks; S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]); }
+          else S.st[s][t] = OPT_UNFIT;
         }
-        __syncwarp();
+        for (unsigned rem = word; rem; rem &= rem - 1) {           // usually ONE lane: plain read-modify-write, in turn
+          if (lane == __ffs(rem) - 1 && ok) {
+            S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term((uint32_t)S.node[t], sc);
+          }
+          __syncwarp();
+        }
         if (lane == 0) S.pmask[s][w] = 0;
       }
       const unsigned long long k = t < nT ? S.tkey[s][t] : 0ull;
@@ -371,7 +373,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
         t = nT++;
         const uint32_t w = key_node(win);
         if (lane < EGS_G) S.rc[t][lane] = cd.rc[lane]; else if (lane < 2 * EGS_G) S.rm[t][lane - EGS_G] = cd.rm[lane - EGS_G];
-        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = cd.mt; S.dirty[t] = 0; }
+        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = cd.mt; S.dirty[t] = 0; S.fterm[t] = fit_term(w); }
         {
           uint8_t st = cd.st[lane];                                // lane == shape index
           if (st == OPT_NEW && S.observed[lane]) st = OPT_CACHED;
@@ -395,7 +397,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
       int ok = 0;
       if (lane == 0) {
         S.st[s][t] = OPT_ABSENT; S.tkey[s][t] = 0; S.pmask[s][t >> 5] |= pbit;    // deferred delete, node.go:90-92
-        S.afit[s] = fitc - 1; S.afd[s] = ofd - fit_term((uint32_t)o_node); S.asd[s] = osd - score_term((uint32_t)o_node, key_score(win));
+        S.afit[s] = fitc - 1; S.afd[s] = ofd - S.fterm[t]; S.asd[s] = osd - score_term((uint32_t)o_node, key_score(win));
         if (single) {                                               // GPUs.Transact gpu.go:164-171
           const int g = __ffs(masks) - 1;
           const int c = S.rc[t][g], m = S.rm[t][g], rc = S.rq_core[s], rm = S.rq_mem[s];
@@ -414,7 +416,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
         else if (v == OPT_NEW && !S.observed[lane]) {
           const unsigned long long k2 = S.tkey[lane][t];
           S.st[lane][t] = OPT_ABSENT; S.tkey[lane][t] = 0; S.pmask[lane][t >> 5] |= pbit;
-          S.afit[lane] -= 1; S.afd[lane] -= fit_term((uint32_t)o_node); S.asd[lane] -= score_term((uint32_t)o_node, key_score(k2));
+          S.afit[lane] -= 1; S.afd[lane] -= S.fterm[t]; S.asd[lane] -= score_term((uint32_t)o_node, key_score(k2));
         }
       }
       __syncwarp();

@@ -167,6 +167,9 @@ int egs_schedule_batch_device(egs_handle *h, int mode, int n_pods, const int32_t
  * shard order.  Every rank issues the same calls; the batch loop exchanges the
  * per-shape candidate lists with ncclAllGather once per round. */
 int egs_shard_set(egs_handle *h, int rank, int world);
+/* The contiguous node range [lo, hi) egs_shard_set gives rank `rank` of `world` (pure host
+ * arithmetic, no handle): boundaries are multiples of 128, the last shard ends at max_nodes. */
+int egs_shard_range(int max_nodes, int rank, int world, int *lo, int *hi);
 int egs_comm_unique_id(uint8_t out_id[128]);
 int egs_comm_init(egs_handle *h, const uint8_t id[128]);
 
