@@ -50,6 +50,23 @@ def build_synth(force: bool = False) -> str:
     return LIBSYNTH
 
 
+LIBHOST = os.path.join(LIBDIR, "libegs_host.so")
+
+
+def build_host(force: bool = False) -> str:
+    """C++ mirror of the reference's ResourceScheduler plugin interface over the C ABI."""
+    hdir = os.path.join(CSRC, "host")
+    srcs = sorted(glob.glob(os.path.join(hdir, "*.cc")) + glob.glob(os.path.join(hdir, "*.h")) +
+                  [os.path.join(ROOT, "include", "egs.h")])
+    build_libegs(force)
+    if force or _stale(LIBHOST, srcs + [LIBEGS]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-o", LIBHOST] +
+                              sorted(glob.glob(os.path.join(hdir, "*.cc"))) +
+                              ["-L" + LIBDIR, "-legs", "-Wl,-rpath,$ORIGIN"])
+    return LIBHOST
+
+
 def build_all(force: bool = False) -> None:
     build_synth(force)
     build_libegs(force)
+    build_host(force)

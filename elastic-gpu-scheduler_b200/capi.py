@@ -24,7 +24,7 @@ SYMBOLS = [
     "egs_create", "egs_destroy", "egs_last_error", "egs_status_string", "egs_unit_from_requests",
     "egs_node_set_allocatable", "egs_node_set", "egs_state_load", "egs_state_load_bulk", "egs_state_dump",
     "egs_state_snapshot", "egs_state_restore",
-    "egs_filter", "egs_score", "egs_bind", "egs_option_peek", "egs_pod_apply", "egs_pod_cancel",
+    "egs_filter", "egs_score", "egs_bind", "egs_option_peek", "egs_pod_apply", "egs_node_replay_pod", "egs_pod_cancel",
     "egs_pod_known", "egs_pod_released", "egs_schedule_batch", "egs_schedule_batch_device",
     "egs_shard_set", "egs_shard_range", "egs_comm_unique_id", "egs_comm_init", "egs_profile_evaluate", "egs_profile_get",
     "egs_profile_reset", "egs_get_stream", "egs_rounds_stats", "egs_mix64",
@@ -71,6 +71,7 @@ def load(build: bool = True):
     L.egs_bind.argtypes = [vp, i32, i32, vp, u64, vp]
     L.egs_option_peek.argtypes = [vp, i32, i32, vp, vp, vp, vp]
     L.egs_pod_apply.argtypes = [vp, i32, i32, vp, vp, vp, u64]
+    L.egs_node_replay_pod.argtypes = [vp, i32, i32, vp, vp, vp, u64]
     L.egs_pod_cancel.argtypes = [vp, i32, i32, vp, vp, vp, u64]
     L.egs_pod_known.argtypes = [vp, u64]
     L.egs_pod_released.argtypes = [vp, u64]

@@ -571,6 +571,22 @@ extern "C" int egs_pod_apply(egs_handle *h, int node_id, int n_containers, const
   return EGS_OK;
 }
 
+// NodeAllocator.Add(pod, nil) node.go:148-160 (replay at node load, node.go:52-54)
+extern "C" int egs_node_replay_pod(egs_handle *h, int node_id, int n_containers, const egs_unit *units,
+                                   const int32_t *alloc_off, const int32_t *alloc_idx, uint64_t uid) {
+  if (!h) return EGS_ERR_BAD_ARG;
+  Guard g(h);
+  if (node_id < 0 || node_id >= h->max_nodes) return EGS_ERR_BAD_ARG;
+  if (h->h_gpu_count[node_id] == 0) return EGS_ERR_NO_NODE;
+  TRY(check_units(n_containers, units));
+  TRY(flush_pending(h));
+  if (!h->pods_map.count(NodeUid{node_id, uid})) {
+    TRY(apply_lists(h, 0, node_id, n_containers, units, alloc_off, alloc_idx));
+    h->pods_map.insert(NodeUid{node_id, uid});
+  }
+  return EGS_OK;
+}
+
 // ForgetPod scheduler.go:247-267
 extern "C" int egs_pod_cancel(egs_handle *h, int node_id, int n_containers, const egs_unit *units,
                               const int32_t *alloc_off, const int32_t *alloc_idx, uint64_t uid) {

@@ -121,6 +121,11 @@ int egs_option_peek(egs_handle *h, int node_id, int n_containers, const egs_unit
  * GPU indices of container c in annotation order. */
 int egs_pod_apply(egs_handle *h, int node_id, int n_containers, const egs_unit *units,
                   const int32_t *alloc_off, const int32_t *alloc_idx, uint64_t uid);
+/* NodeAllocator.Add(pod, nil) alone (node.go:148-160), as NewNodeAllocator replays the pods already
+ * assumed on a node when it is first loaded (node.go:52-54): node-level podsMap + Transact, the
+ * scheduler-level podMaps is not touched. */
+int egs_node_replay_pod(egs_handle *h, int node_id, int n_containers, const egs_unit *units,
+                        const int32_t *alloc_off, const int32_t *alloc_idx, uint64_t uid);
 /* ForgetPod (scheduler.go:247-267 -> node.go:129-140 -> gpu.go:177-191); node_id < 0 == empty NodeName. */
 int egs_pod_cancel(egs_handle *h, int node_id, int n_containers, const egs_unit *units,
                    const int32_t *alloc_off, const int32_t *alloc_idx, uint64_t uid);
