@@ -260,6 +260,7 @@ struct ResolveSmem {                 // shape-major, padded: lanes = tracked slo
   uint32_t al[RS][RT + 1];                // option.Allocated masks
   uint8_t st[RS][RT + 4];                 // OPT_*
   unsigned pmask[RS][RTW];                // tracked slots whose option is ABSENT: Trade at the shape's next pod
+  unsigned long long hkey[RS][RD];        // current head of each list (0 = none)
   unsigned long long afd[RS], asd[RS];
   int afit[RS];
   int cur[RS][RD], len[RS][RD], more[RS][RD];
@@ -268,15 +269,41 @@ struct ResolveSmem {                 // shape-major, padded: lanes = tracked slo
   int node[RT], mt[RT], dirty[RT];
   unsigned long long fterm[RT];           // fit_term(node) of each tracked slot
   int rc[RT][EGS_G], rm[RT][EGS_G];
+  // per-pod outputs, flushed 32 pods at a time with coalesced stores
+  int o_node[32], o_status[32], o_fit[32]; uint32_t o_alloc[32]; unsigned long long o_fd[32], o_sd[32];
   Req reqs[RS];
 };
+
+// advance list (s, d) past consumed entries and cache its head
+__device__ __forceinline__ void list_head_update(ResolveSmem &S, int s, int d) {
+  int c = S.cur[s][d];
+  const int len = S.len[s][d];
+  while (c < len && S.lkey[s][d * RK + c] == 0) c++;
+  S.cur[s][d] = c;
+  S.hkey[s][d] = c < len ? S.lkey[s][d * RK + c] : 0ull;
+}
+
+__device__ __forceinline__ void flush_outputs(const ResolveSmem &S, const PodOut &out, int p_first, int n, int lane) {
+  if (lane < n) {
+    const size_t p = (size_t)p_first + lane;
+    if (out.node) out.node[p] = S.o_node[lane];
+    if (out.status) out.status[p] = S.o_status[lane];
+    if (out.fit_count) out.fit_count[p] = S.o_fit[lane];
+    if (out.fit_digest) out.fit_digest[p] = S.o_fd[lane];
+    if (out.score_digest) out.score_digest[p] = S.o_sd[lane];
+    if (out.alloc) reinterpret_cast<uint32_t *>(out.alloc)[p] = S.o_alloc[lane];
+  }
+}
 
 __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(smem_raw);
   const int lane = threadIdx.x;
   const int D = a.n_shards, ns = a.set.n, DK = D * RK;
+  const int grp = lane >> 3, gl = lane & 7;                      // 8-lane groups: one lane per GPU of a node
+  const unsigned gmask = 0xFFu << (8 * grp);
   // ---- prologue
+  bool mono = true;                                              // all requests >= 0: rows only decrease in this round
   {
     const int s = lane;                                          // RS == 32: one shape per lane
     int fit = 0; unsigned long long fd = 0, sd = 0;
@@ -292,37 +319,39 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
       const Req &r = a.reqs[s];
       S.rq_single[s] = req_is_single(r); S.rq_core[s] = r.core[0]; S.rq_mem[s] = r.mem[0];
       S.rq_cmask[s] = r.C >= 4 ? 0xFFFFFFFFu : ((1u << (8 * r.C)) - 1u);   // alloc planes >= C are never written
+      for (int c = 0; c < r.C; c++) mono &= r.core[c] >= 0 && r.mem[c] >= 0;
     }
   }
+  mono = __all_sync(0xffffffffu, mono);
   for (int s = 0; s < ns; s++)
     for (int e = lane; e < DK; e += 32) S.lkey[s][e] = a.bufs[e / RK].cand[s][e % RK].key;
   __syncwarp();
-  int nT = 0, done = 0, reason = 0;
+  for (int i = lane; i < ns * D; i += 32) list_head_update(S, i / D, i % D);
+  __syncwarp();
+  int nT = 0, done = 0, reason = 0, n_observed = 0, flushed = 0;
   const int my_set_slot = lane < ns ? a.set.slot[lane] : -1;
   int myslots = -1;
   // ---- sequential replay
   for (int p = a.p0; p < a.p_limit; p++) {
     const int rel = p - a.p0;
-    if ((rel & 31) == 0) myslots = (p + lane < a.p_limit) ? a.pod_slot[p + lane] : -1;   // one L2 trip per 32 pods
+    if ((rel & 31) == 0) {
+      if (rel) { flush_outputs(S, a.out, a.p0 + flushed, 32, lane); flushed += 32; }
+      myslots = (p + lane < a.p_limit) ? a.pod_slot[p + lane] : -1;   // one L2 trip per 32 pods
+    }
     const int pslot = __shfl_sync(0xffffffffu, myslots, rel & 31);
     const unsigned mb = __ballot_sync(0xffffffffu, my_set_slot == pslot);
     if (!mb) { reason = 1; break; }                              // shape outside this round's set
     const int s = __ffs(mb) - 1;
     if (nT >= RT) { reason = 2; break; }                          // no free tracked slot for a new winner
-    // best untracked candidate per shard (lists are sorted; consumed entries are zeroed)
-    unsigned long long head = 0; bool dry = false; int hk = 0;
-    if (lane < D) {
-      int c = S.cur[s][lane];
-      const int len = S.len[s][lane];
-      while (c < len && S.lkey[s][lane * RK + c] == 0) c++;
-      S.cur[s][lane] = c;
-      if (c < len) { head = S.lkey[s][lane * RK + c]; hk = c; } else dry = S.more[s][lane] != 0;
-    }
+    // best untracked candidate per shard (cached heads; consumed entries were skipped when they were zeroed)
+    unsigned long long head = 0; bool dry = false;
+    if (lane < D) { head = S.hkey[s][lane]; dry = head == 0 && S.more[s][lane] != 0; }
     if (__ballot_sync(0xffffffffu, dry)) { reason = 3; break; }   // a truncated list ran dry: next round
     if (!S.observed[s]) {                                          // first pod of this shape in the round:
       for (int t = lane; t < nT; t += 32) if (S.st[s][t] == OPT_NEW) S.st[s][t] = OPT_CACHED;   // NEW options are now ordinary
       __syncwarp();
       if (lane == 0) S.observed[s] = 1;
+      n_observed++;
       __syncwarp();
     }
     const int single = S.rq_single[s];
@@ -330,25 +359,66 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
     unsigned long long best = 0; int best_t = -1;
     const int nw = (nT + 31) >> 5;
     for (int w = 0; w < nw; w++) {
-      const unsigned word = S.pmask[s][w];
-      const int t = w * 32 + lane;
+      unsigned word = S.pmask[s][w];
       if (word) {
-        bool ok = false; int sc = 0;
-        if ((word >> lane) & 1u) {
-          uint32_t masks;
-          if (single) { int g; ok = trade_single(S.rc[t], S.rm[t], S.rq_core[s], S.rq_mem[s], a.policy, sc, g); masks = 1u << g; }
-          else ok = trade_general(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], a.policy, sc, masks);
-          if (ok) { S.st[s][t] = OPT_CACHED; S.al[s][t] = masks; S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]); }
-          else S.st[s][t] = OPT_UNFIT;
-        }
-        for (unsigned rem = word; rem; rem &= rem - 1) {           // usually ONE lane: plain read-modify-write, in turn
-          if (lane == __ffs(rem) - 1 && ok) {
-            S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term((uint32_t)S.node[t], sc);
+        if (single) {
+          // 8 lanes per pending node (lane == GPU), up to 4 nodes at a time
+          const int rq_c = S.rq_core[s], rq_m = S.rq_mem[s];
+          while (word) {
+            int bsel = -1;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const int b = word ? __ffs(word) - 1 : -1;
+              if (word) word &= word - 1;
+              if (q == grp) bsel = b;
+            }
+            bool okl = false; int sc = 0; int t = 0;
+            if (bsel >= 0) {                                       // group-uniform
+              t = w * 32 + bsel;
+              const int c = S.rc[t][gl], m = S.rm[t][gl];
+              const int cmin = (int)__reduce_min_sync(gmask, (unsigned)c), mmin = (int)__reduce_min_sync(gmask, (unsigned)m);
+              const int c1 = __reduce_max_sync(gmask, c), m1 = __reduce_max_sync(gmask, m);
+              const int c2 = __reduce_max_sync(gmask, c == c1 ? INT32_MIN : c), m2 = __reduce_max_sync(gmask, m == m1 ? INT32_MIN : m);
+              const bool cu = __popc(__ballot_sync(gmask, c == c1)) == 1, mu = __popc(__ballot_sync(gmask, m == m1)) == 1;
+              const int cex = (c == c1 && cu) ? c2 : c1, mex = (m == m1 && mu) ? m2 : m1;   // max over the OTHER GPUs
+              const bool ok = c >= rq_c && m >= rq_m;                                         // gpu.go:55
+              const int nc = c - rq_c, nm = m - rq_m;
+              const int x = (max(mex, nm) + max(cex, nc)) - (min(mmin, nm) + min(cmin, nc));
+              const int key = !ok ? -1 : (a.policy == EGS_BINPACK ? (x >> 2) * 8 + gl : gl);
+              const int bk = __reduce_max_sync(gmask, key);
+              if (gl == 0) {
+                if (bk >= 0) {
+                  sc = a.policy == EGS_BINPACK ? (bk >> 3) * 100 : 0;
+                  S.st[s][t] = OPT_CACHED; S.al[s][t] = 1u << (bk & 7); S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]);
+                  okl = true;
+                } else {
+                  S.st[s][t] = OPT_UNFIT;
+                }
+              }
+            }
+            for (unsigned rem = __ballot_sync(0xffffffffu, okl); rem; rem &= rem - 1) {   // usually one leader
+              if (lane == __ffs(rem) - 1) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term((uint32_t)S.node[t], sc); }
+              __syncwarp();
+            }
           }
-          __syncwarp();
+        } else {
+          const int t = w * 32 + lane;
+          bool ok = false; int sc = 0;
+          if ((word >> lane) & 1u) {
+            uint32_t masks;
+            ok = trade_general(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], a.policy, sc, masks);
+            if (ok) { S.st[s][t] = OPT_CACHED; S.al[s][t] = masks; S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]); }
+            else S.st[s][t] = OPT_UNFIT;
+          }
+          for (unsigned rem = word; rem; rem &= rem - 1) {
+            if (lane == __ffs(rem) - 1 && ok) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term((uint32_t)S.node[t], sc); }
+            __syncwarp();
+          }
         }
+        __syncwarp();
         if (lane == 0) S.pmask[s][w] = 0;
       }
+      const int t = w * 32 + lane;
       const unsigned long long k = t < nT ? S.tkey[s][t] : 0ull;
       if (k > best) { best = k; best_t = t; }
     }
@@ -368,8 +438,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
       int t;
       if (__shfl_sync(0xffffffffu, (int)from_head, owner)) {
         // an untracked node wins: it becomes tracked (payload from the candidate buffer)
-        const int k = __shfl_sync(0xffffffffu, hk, owner);
-        const Cand &cd = a.bufs[owner].cand[s][k];
+        const Cand &cd = a.bufs[owner].cand[s][S.cur[s][owner]];
         t = nT++;
         const uint32_t w = key_node(win);
         if (lane < EGS_G) S.rc[t][lane] = cd.rc[lane]; else if (lane < 2 * EGS_G) S.rm[t][lane - EGS_G] = cd.rm[lane - EGS_G];
@@ -386,6 +455,8 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
             const unsigned long long q = S.lkey[s2][e];
             if (q != 0 && key_node(q) == w) S.lkey[s2][e] = 0;
           }
+        __syncwarp();
+        for (int i = lane; i < ns * D; i += 32) list_head_update(S, i / D, i % D);
         __syncwarp();
       } else {
         t = __shfl_sync(0xffffffffu, best_t, owner);
@@ -409,10 +480,12 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
         S.dirty[t] = 1;
       }
       ok = __shfl_sync(0xffffffffu, ok, 0);
-      // rows changed: UNFIT memos and not-yet-observed NEW options of this node are void
-      if (lane < ns && lane != s) {
+      // Rows changed.  (a) not-yet-observed NEW options of this node are void (only while some shape of the
+      // round is unobserved); (b) UNFIT memos are void -- unless every request of the round is >= 0: rows
+      // then only decrease and an option that did not fit can never fit (exact shortcut).
+      if ((!mono || n_observed < ns) && lane < ns && lane != s) {
         const uint8_t v = S.st[lane][t];
-        if (v == OPT_UNFIT) { S.st[lane][t] = OPT_ABSENT; S.pmask[lane][t >> 5] |= pbit; }
+        if (v == OPT_UNFIT && !mono) { S.st[lane][t] = OPT_ABSENT; S.pmask[lane][t >> 5] |= pbit; }
         else if (v == OPT_NEW && !S.observed[lane]) {
           const unsigned long long k2 = S.tkey[lane][t];
           S.st[lane][t] = OPT_ABSENT; S.tkey[lane][t] = 0; S.pmask[lane][t >> 5] |= pbit;
@@ -424,16 +497,13 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
       o_masks = ok ? masks : 0;
     }
     if (lane == 0) {
-      if (a.out.node) a.out.node[p] = o_node;
-      if (a.out.status) a.out.status[p] = o_status;
-      if (a.out.fit_count) a.out.fit_count[p] = fitc;
-      if (a.out.fit_digest) a.out.fit_digest[p] = ofd;
-      if (a.out.score_digest) a.out.score_digest[p] = osd;
-      if (a.out.alloc) *reinterpret_cast<uint32_t *>(a.out.alloc + (size_t)p * EGS_C) = o_masks;
+      const int r = rel & 31;
+      S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fitc; S.o_fd[r] = ofd; S.o_sd[r] = osd; S.o_alloc[r] = o_masks;
     }
     done++;
   }
   __syncwarp();
+  flush_outputs(S, a.out, a.p0 + flushed, done - flushed, lane);
   // ---- epilogue: write the tracked nodes back (each shard its own nodes)
   for (int t = 0; t < nT; t++) {
     const int w = S.node[t];

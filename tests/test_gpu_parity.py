@@ -152,3 +152,60 @@ def test_full_size_properties(cfg):
     _conservation(w, b, e2)
     assert (b["status"] != 1).all()   # the named clusters have room for every pod (no NOFIT);
     # status 3 (stale cached option, gpu.go:158-168) is reference behaviour and does occur under spread
+
+
+def _random_batch(seed, n_nodes, n_pods, n_shapes, policy):
+    """Mixed shapes: fractional, whole-GPU (count 1..2), -1 sentinel containers, 1..4 containers per pod;
+    heterogeneous nodes (G in 1,2,4,8).  Non-monotone rounds: sentinel units ADD 1 to a GPU (gpu.go:36-37)."""
+    import oracle_c as oc
+    rng = np.random.default_rng(seed)
+    eg = _egs()
+    e = eg.Egs(policy, n_nodes)
+    o = oc.OracleC(policy)
+    for n in range(n_nodes):
+        g = int(rng.choice([1, 2, 4, 8]))
+        m = int(rng.choice([16, 40, 80]))
+        assert o.add_node(100 * g, m * g) == n
+        assert e.node_set_allocatable(n, 100 * g, m * g) == 0
+        if rng.integers(0, 2):
+            core = [int(rng.choice([100, 100, 60, 30, 0])) for _ in range(g)]
+            mem = [int(rng.integers(0, m + 1)) for _ in range(g)]
+            o.set_rows(n, core, mem)
+            assert e.state_load(n, core, mem) == 0
+    shapes = []
+    for _ in range(n_shapes):
+        c = int(rng.integers(1, 5))
+        units = []
+        for _ in range(c):
+            k = rng.integers(0, 10)
+            if k == 0:
+                units.append((-1, -1, 0))
+            elif k == 1:
+                units.append((0, 0, int(rng.integers(1, 3))))
+            else:
+                units.append((int(rng.choice([0, 5, 10, 25, 50])), int(rng.integers(1, 12)), 0))
+        shapes.append(units)
+    pick = rng.integers(0, n_shapes, n_pods)
+    c_off = [0]
+    units = []
+    for s in pick:
+        units.extend(shapes[int(s)])
+        c_off.append(len(units))
+    return e, o, np.array(c_off, np.int32), np.array(units, np.int32)
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+@pytest.mark.parametrize("seed,n_nodes,n_pods,n_shapes", [(1, 50, 3000, 6), (2, 300, 4000, 12), (3, 2000, 3000, 40), (4, 20, 2000, 3)])
+def test_batch_mixed_shapes_vs_oracle(seed, n_nodes, n_pods, n_shapes, policy):
+    for mode in (1, 2):
+        e, o, c_off, units = _random_batch(seed, n_nodes, n_pods, n_shapes, policy)
+        ref = o.schedule_batch(c_off, units.astype(np.int64))
+        got = e.schedule_batch(c_off, units, mode=mode)
+        for f in FIELDS:
+            assert np.array_equal(ref[f], got[f]), f"mode {mode}: {f} differs first at pod {np.argwhere(ref[f] != got[f])[:1]}"
+        core, mem, gc, _ = e.state_dump()
+        for n in range(n_nodes):
+            rows = o.rows(n)
+            assert [int(x) for x in core[n, :gc[n]]] == [r[0] for r in rows]
+            assert [int(x) for x in mem[n, :gc[n]]] == [r[1] for r in rows]
+        assert (ref["status"] == 3).sum() > 0 or n_nodes > 1000
