@@ -13,7 +13,7 @@ LIBDIR = os.path.join(PKG, "lib")
 LIBEGS = os.path.join(LIBDIR, "libegs.so")
 LIBSYNTH = os.path.join(LIBDIR, "libegs_synth.so")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+NVCC_FLAGS = (["-DEGS_RESOLVE_PROF"] if os.environ.get("EGS_RESOLVE_PROF") else []) + ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 

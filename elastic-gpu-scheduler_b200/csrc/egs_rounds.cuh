@@ -33,7 +33,7 @@
 
 struct RoundSet { int n; int slot[RS]; };
 
-struct Cand {                       // payload of one candidate node
+struct alignas(16) Cand {           // payload of one candidate node (16-byte chunks: cp.async)
   unsigned long long key;           // cand_key(score, node); 0 = empty
   int32_t rc[EGS_G], rm[EGS_G];
   int32_t mt, pad;
@@ -41,10 +41,10 @@ struct Cand {                       // payload of one candidate node
   uint32_t al[RS];
   uint8_t st[RS];
 };
-struct ShardBuf {                   // what one shard contributes to a round
+struct alignas(16) ShardBuf {       // what one shard contributes to a round
   int32_t len[RS], more[RS], fit[RS], pad0;
   unsigned long long fd[RS], sd[RS];
-  Cand cand[RS][RK];
+  alignas(16) Cand cand[RS][RK];
 };
 
 struct AggPart { unsigned long long fd, sd; int fit, pad; };
@@ -251,6 +251,7 @@ struct ResolveArgs {
   const int32_t *pod_slot; int p0, p_limit;
   PodOut out;
   int32_t *done;                    // [0] pods resolved, [1] tracked nodes, [2] stop reason
+  long long *prof;                  // EGS_RESOLVE_PROF: 12 counters
 };
 
 #define RTW (RT / 32)
@@ -272,6 +273,8 @@ struct ResolveSmem {                 // shape-major, padded: lanes = tracked slo
   // per-pod outputs, flushed 32 pods at a time with coalesced stores
   int o_node[32], o_status[32], o_fit[32]; uint32_t o_alloc[32]; unsigned long long o_fd[32], o_sd[32];
   Req reqs[RS];
+  int hpay_node[RS];                      // node whose payload sits (or is arriving) in hpay[s]; -1 none
+  alignas(16) Cand hpay[RS];              // prefetched payload of each shape's best untracked head
 };
 
 // advance list (s, d) past consumed entries and cache its head
@@ -295,9 +298,167 @@ __device__ __forceinline__ void flush_outputs(const ResolveSmem &S, const PodOut
   }
 }
 
+#ifdef EGS_RESOLVE_PROF
+#define PROF_T(i) { long long now_ = clock64(); prof[i] += now_ - tprev; tprev = now_; }
+#define PROF_C(i, v) { prof[i] += (v); }
+#define PROF_PTR prof
+#else
+#define PROF_T(i)
+#define PROF_C(i, v)
+#define PROF_PTR nullptr
+#endif
+// Segmented (8-lane group) reductions with FULL-mask shuffles: xor offsets 1,2,4 never leave a group,
+// so all four groups reduce at once.  (Collectives with a different member mask per group are issued
+// one group at a time by the hardware.)
+__device__ __forceinline__ int seg8_max(int v) {
+  v = max(v, __shfl_xor_sync(0xffffffffu, v, 1)); v = max(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return max(v, __shfl_xor_sync(0xffffffffu, v, 4));
+}
+__device__ __forceinline__ unsigned seg8_minu(unsigned v) {
+  v = min(v, __shfl_xor_sync(0xffffffffu, v, 1)); v = min(v, __shfl_xor_sync(0xffffffffu, v, 2));
+  return min(v, __shfl_xor_sync(0xffffffffu, v, 4));
+}
+__device__ __forceinline__ int seg8_add(int v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
+  return v + __shfl_xor_sync(0xffffffffu, v, 4);
+}
+__device__ __forceinline__ unsigned long long seg8_max64(unsigned long long v) {
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o); v = x > v ? x : v; }
+  return v;
+}
+
+// Best untracked head of shape s over the shards -> (key, shard); warp-uniform result.
+__device__ __forceinline__ unsigned long long best_head(const ResolveSmem &S, int s, int D, int &d_out) {
+  unsigned long long b = 0; int bd = 0;
+  for (int d = 0; d < D; d++) { const unsigned long long k = S.hkey[s][d]; if (k > b) { b = k; bd = d; } }
+  d_out = bd;
+  return b;
+}
+// Start the asynchronous copy of that head's payload into S.hpay[s] (23 x 16 B, one chunk per lane).
+__device__ __forceinline__ void prefetch_head(ResolveSmem &S, const ResolveArgs &a, int s, int D, int lane) {
+  int d; const unsigned long long k = best_head(S, s, D, d);
+  if (k == 0) { if (lane == 0) S.hpay_node[s] = -1; return; }
+  const char *src = reinterpret_cast<const char *>(&a.bufs[d].cand[s][S.cur[s][d]]);
+  if (lane < (int)(sizeof(Cand) / 16)) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<char *>(&S.hpay[s]) + lane * 16);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + lane * 16));
+  }
+  if (lane == 0) S.hpay_node[s] = (int)key_node(k);
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct PodRec {                     // decision of one pod, made by an 8-lane group (fast path)
+  int s, u, bk, from_head, t, d, fit, pad;
+  unsigned long long win, fd, sd;
+};
+
+// Commit of one decided pod: NodeAllocator.Allocate (node.go:87-104) on the tracked copy, or NOFIT.
+// (fitc, ofd, osd) are the shape's aggregates after this pod's filter; warp-uniform arguments.
+__device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a, int lane, int rel, int s,
+                                           unsigned long long win, int from_head, int t_in, int d, int fitc,
+                                           unsigned long long ofd, unsigned long long osd, bool mono, int ns, int D,
+                                           int &nT, int n_observed, long long *prof) {
+#ifdef EGS_RESOLVE_PROF
+  long long tprev = clock64();
+#endif
+  const int DK = D * RK;
+  int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
+  if (win != 0) {
+    int t = t_in;
+    if (from_head) {
+      // an untracked node wins: it becomes tracked.  Its payload was prefetched into shared memory when it
+      // became the best head of this shape (cp.async); fall back to the candidate buffer otherwise.
+      t = nT++;
+      const uint32_t w = key_node(win);
+      cp_async_wait_all();
+      __syncwarp();
+      const bool pre = S.hpay_node[s] == (int)w;
+      const Cand &cd = pre ? S.hpay[s] : a.bufs[d].cand[s][S.cur[s][d]];
+      {
+        const int rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0;      // rc[8] and rm[8] are contiguous
+        const int mtv = cd.mt;
+        uint8_t st = cd.st[lane];                                // lane == shape index
+        const int scv = cd.sc[lane]; const uint32_t alv = cd.al[lane];
+        if (lane < EGS_G) S.rc[t][lane] = rowv; else if (lane < 2 * EGS_G) S.rm[t][lane - EGS_G] = rowv;
+        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = mtv; S.dirty[t] = 0; S.fterm[t] = fit_term(w); }
+        if (st == OPT_NEW && S.observed[lane]) st = OPT_CACHED;
+        S.st[lane][t] = st; S.al[lane][t] = alv;
+        S.tkey[lane][t] = (st == OPT_CACHED || st == OPT_NEW) ? cand_key(scv, w) : 0ull;
+        if (st == OPT_ABSENT) S.pmask[lane][t >> 5] |= 1u << (t & 31);
+      }
+      for (int e = lane; e < DK; e += 32) {                       // it leaves every untracked list
+#pragma unroll 4
+        for (int s2 = 0; s2 < ns; s2++) {
+          const unsigned long long q = S.lkey[s2][e];
+          if (q != 0 && key_node(q) == w) S.lkey[s2][e] = 0;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < ns * D; i += 32) list_head_update(S, i / D, i % D);
+      __syncwarp();
+      {                                                            // heads that changed: prefetch their payloads
+        bool need = false;
+        if (lane < ns) { int dd; const unsigned long long k = best_head(S, lane, D, dd); need = (k ? (int)key_node(k) : -1) != S.hpay_node[lane]; }
+        for (unsigned rem = __ballot_sync(0xffffffffu, need); rem; rem &= rem - 1) prefetch_head(S, a, __ffs(rem) - 1, D, lane);
+        cp_async_commit();
+      }
+      PROF_T(10) PROF_C(11, 1)
+    }
+    o_node = S.node[t];
+    const int single = S.rq_single[s];
+    const uint32_t masks = S.al[s][t] & S.rq_cmask[s];
+    const unsigned pbit = 1u << (t & 31);
+    int ok = 0;
+    // deferred delete of the option (node.go:90-92) + aggregates: computed by every lane (broadcast loads),
+    // stored by lane 0 -- no divergent region on the common single-container path
+    const int nfit = fitc - 1;
+    const unsigned long long nfd = ofd - S.fterm[t], nsd = osd - score_term((uint32_t)o_node, key_score(win));
+    const unsigned npm = S.pmask[s][t >> 5] | pbit;
+    if (single) {                                                 // GPUs.Transact gpu.go:164-171
+      const int g = __ffs(masks) - 1;
+      const int c = S.rc[t][g], m = S.rm[t][g], rc = S.rq_core[s], rm = S.rq_mem[s];
+      ok = (c >= rc && m >= rm) ? 1 : 0;
+      if (lane == 0) {
+        S.st[s][t] = OPT_ABSENT; S.tkey[s][t] = 0; S.pmask[s][t >> 5] = npm;
+        S.afit[s] = nfit; S.afd[s] = nfd; S.asd[s] = nsd; S.dirty[t] = 1;
+        if (ok) { S.rc[t][g] = c - rc; S.rm[t][g] = m - rm; }
+      }
+    } else {
+      if (lane == 0) {
+        S.st[s][t] = OPT_ABSENT; S.tkey[s][t] = 0; S.pmask[s][t >> 5] = npm;
+        S.afit[s] = nfit; S.afd[s] = nfd; S.asd[s] = nsd; S.dirty[t] = 1;
+        ok = transact_row(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], masks) ? 1 : 0;
+      }
+      ok = __shfl_sync(0xffffffffu, ok, 0);
+    }
+    // Rows changed.  (a) not-yet-observed NEW options of this node are void (only while some shape of the
+    // round is unobserved); (b) UNFIT memos are void -- unless every request of the round is >= 0: rows
+    // then only decrease and an option that did not fit can never fit (exact shortcut).
+    if ((!mono || n_observed < ns) && lane < ns && lane != s) {
+      const uint8_t v = S.st[lane][t];
+      if (v == OPT_UNFIT && !mono) { S.st[lane][t] = OPT_ABSENT; S.pmask[lane][t >> 5] |= pbit; }
+      else if (v == OPT_NEW && !S.observed[lane]) {
+        const unsigned long long k2 = S.tkey[lane][t];
+        S.st[lane][t] = OPT_ABSENT; S.tkey[lane][t] = 0; S.pmask[lane][t >> 5] |= pbit;
+        S.afit[lane] -= 1; S.afd[lane] -= S.fterm[t]; S.asd[lane] -= score_term((uint32_t)o_node, key_score(k2));
+      }
+    }
+    __syncwarp();
+    o_status = ok ? EGS_OK : EGS_ERR_TRANSACT;
+    o_masks = ok ? masks : 0;
+  }
+  if (lane == 0) {
+    const int r = rel & 31;
+    S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fitc; S.o_fd[r] = ofd; S.o_sd[r] = osd; S.o_alloc[r] = o_masks;
+  }
+}
+
 __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(smem_raw);
+  __shared__ PodRec recs[4];
   const int lane = threadIdx.x;
   const int D = a.n_shards, ns = a.set.n, DK = D * RK;
   const int grp = lane >> 3, gl = lane & 7;                      // 8-lane groups: one lane per GPU of a node
@@ -328,16 +489,135 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
   __syncwarp();
   for (int i = lane; i < ns * D; i += 32) list_head_update(S, i / D, i % D);
   __syncwarp();
+  for (int s = 0; s < ns; s++) prefetch_head(S, a, s, D, lane);
+  cp_async_commit();
   int nT = 0, done = 0, reason = 0, n_observed = 0, flushed = 0;
   const int my_set_slot = lane < ns ? a.set.slot[lane] : -1;
   int myslots = -1;
   // ---- sequential replay
-  for (int p = a.p0; p < a.p_limit; p++) {
+  int p = a.p0;
+#ifdef EGS_RESOLVE_PROF
+  long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64();
+#endif
+  while (p < a.p_limit) {
     const int rel = p - a.p0;
     if ((rel & 31) == 0) {
       if (rel) { flush_outputs(S, a.out, a.p0 + flushed, 32, lane); flushed += 32; }
       myslots = (p + lane < a.p_limit) ? a.pod_slot[p + lane] : -1;   // one L2 trip per 32 pods
     }
+    // ======== fast path: up to 4 consecutive pods with distinct single-container shapes, decided by four
+    // 8-lane groups at once.  Preconditions make the decisions independent of each other's commits except
+    // for the hazards checked below; requires rows to be monotone and every shape of the round observed.
+    if (mono && n_observed == ns && nT + 4 <= RT && (rel & 31) <= 28) {
+      int sq[4]; int W = 0;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const int pslot = __shfl_sync(0xffffffffu, myslots, (rel & 31) + q);
+        const unsigned mb = __ballot_sync(0xffffffffu, my_set_slot == pslot && pslot >= 0);
+        sq[q] = mb ? __ffs(mb) - 1 : -1;
+      }
+      {
+        bool okq = true;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          okq = okq && sq[q] >= 0 && p + q < a.p_limit;
+          for (int i = 0; i < q; i++) okq = okq && sq[q] != sq[i];
+          if (okq) W = q + 1;
+        }
+      }
+      const int sg = grp == 0 ? sq[0] : grp == 1 ? sq[1] : grp == 2 ? sq[2] : max(sq[3], 0);
+      const int sgs = max(sg, 0);                                  // safe index for inactive groups
+      // per group: single shape? at most one pending slot? list dry?   (all lanes execute; no group masks)
+      unsigned long long head = 0; int u;
+      {
+        const unsigned word = gl < ((nT + 31) >> 5) ? S.pmask[sgs][gl] : 0u;
+        const int cnt = seg8_add(__popc(word));
+        u = seg8_max(word ? gl * 32 + __ffs(word) - 1 : -1);
+        bool dry = false;
+        if (gl < D) { head = S.hkey[sgs][gl]; dry = head == 0 && S.more[sgs][gl] != 0; }
+        const bool bad = cnt > 1 || !S.rq_single[sgs] || dry;
+        const unsigned badm = __ballot_sync(0xffffffffu, bad);
+#pragma unroll
+        for (int q = 3; q >= 0; q--) if ((badm >> (8 * q)) & 0xFFu) W = min(W, q);
+      }
+      PROF_T(0)
+      if (W >= 2) {
+        // ---- decisions (read-only on shared state); groups >= W compute on a valid shape and are ignored
+        {
+          const int rq_c = S.rq_core[sgs], rq_m = S.rq_mem[sgs];
+          const int uu = max(u, 0);
+          // Trade of the one absent option, lane == GPU
+          const int c = S.rc[uu][gl], m = S.rm[uu][gl];
+          const int cmin = (int)seg8_minu((unsigned)c), mmin = (int)seg8_minu((unsigned)m);
+          const int c1 = seg8_max(c), m1 = seg8_max(m);
+          const int c2 = seg8_max(c == c1 ? INT32_MIN : c), m2 = seg8_max(m == m1 ? INT32_MIN : m);
+          const unsigned ceq = (__ballot_sync(0xffffffffu, c == c1) >> (8 * grp)) & 0xFFu;
+          const unsigned meq = (__ballot_sync(0xffffffffu, m == m1) >> (8 * grp)) & 0xFFu;
+          const int cex = (c == c1 && __popc(ceq) == 1) ? c2 : c1, mex = (m == m1 && __popc(meq) == 1) ? m2 : m1;
+          const bool ok = c >= rq_c && m >= rq_m;
+          const int nc = c - rq_c, nm = m - rq_m;
+          const int x = (max(mex, nm) + max(cex, nc)) - (min(mmin, nm) + min(cmin, nc));
+          const int key = (!ok || u < 0) ? -1 : (a.policy == EGS_BINPACK ? (x >> 2) * 8 + gl : gl);
+          const int bk = seg8_max(key);
+          const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
+          const uint32_t nd = (uint32_t)S.node[uu];
+          const unsigned long long tradekey = bk >= 0 ? cand_key(sc, nd) : 0ull;
+          unsigned long long best = 0; int best_t = -1;
+          for (int t = gl; t < nT; t += 8) {                       // the pending slot holds key 0 (zeroed by its bind)
+            const unsigned long long k = S.tkey[sgs][t];
+            if (k > best) { best = k; best_t = t; }
+          }
+          if (tradekey > best) { best = tradekey; best_t = u; }
+          const bool from_head = head > best;
+          const unsigned long long mine = from_head ? head : best;
+          const unsigned long long win = seg8_max64(mine);
+          const unsigned wm = (__ballot_sync(0xffffffffu, mine == win && win != 0) >> (8 * grp)) & 0xFFu;
+          const int ownl = wm ? __ffs(wm) - 1 : 0;                   // lane inside the group
+          const int fh = __shfl_sync(0xffffffffu, (int)from_head, grp * 8 + ownl);
+          const int tw = __shfl_sync(0xffffffffu, best_t, grp * 8 + ownl);
+          if (gl == 0 && grp < W) {
+            PodRec r;
+            r.s = sg; r.u = u; r.bk = bk; r.from_head = fh; r.t = tw; r.d = ownl; r.pad = sc;
+            r.fit = S.afit[sgs] + (bk >= 0); r.fd = S.afd[sgs] + (bk >= 0 ? S.fterm[uu] : 0ull);
+            r.sd = S.asd[sgs] + (bk >= 0 ? score_term(nd, sc) : 0ull); r.win = win;
+            recs[grp] = r;
+          }
+        }
+        __syncwarp();
+        PROF_T(1)
+        // ---- hazards: a head-win changes lists / the tracked set for everyone after it; a pending node
+        // that an earlier pod of the group binds must be Traded on the rows AFTER that bind.
+        int Wc = W;
+        {
+          int hfh[4], ht[4], hu[4];
+#pragma unroll
+          for (int q = 0; q < 4; q++) { hfh[q] = recs[q].win != 0 && recs[q].from_head; ht[q] = recs[q].win != 0 ? recs[q].t : -2; hu[q] = recs[q].u; }
+#pragma unroll
+          for (int j = 3; j >= 1; j--) {
+            bool hz = false;
+#pragma unroll
+            for (int i = 0; i < j; i++) hz |= hfh[i] || (hu[j] >= 0 && hu[j] == ht[i]);
+            if (hz && j < Wc) Wc = j;
+          }
+        }
+        PROF_T(2)
+        // ---- commits, in pod order
+        for (int q = 0; q < Wc; q++) {
+          const PodRec r = recs[q];
+          if (r.u >= 0 && lane == 0) {                             // this pod's filter Traded slot u
+            if (r.bk >= 0) { S.st[r.s][r.u] = OPT_CACHED; S.al[r.s][r.u] = 1u << (r.bk & 7); S.tkey[r.s][r.u] = cand_key(r.pad, (uint32_t)S.node[r.u]); }
+            else S.st[r.s][r.u] = OPT_UNFIT;
+            S.pmask[r.s][r.u >> 5] &= ~(1u << (r.u & 31));
+          }
+          __syncwarp();
+          commit_pod(S, a, lane, rel + q, r.s, r.win, r.from_head, r.t, r.d, r.fit, r.fd, r.sd, mono, ns, D, nT, n_observed, PROF_PTR);
+        }
+        PROF_T(3) PROF_C(6, 1) PROF_C(7, Wc) PROF_C(8, W)
+        p += Wc; done += Wc;
+        continue;
+      }
+    }
+    // ======== general path: one pod
     const int pslot = __shfl_sync(0xffffffffu, myslots, rel & 31);
     const unsigned mb = __ballot_sync(0xffffffffu, my_set_slot == pslot);
     if (!mb) { reason = 1; break; }                              // shape outside this round's set
@@ -430,77 +710,16 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
     const unsigned m1 = __reduce_max_sync(0xffffffffu, hi);
     const unsigned m2 = __reduce_max_sync(0xffffffffu, hi == m1 ? (unsigned)mine : 0u);
     const unsigned long long win = ((unsigned long long)m1 << 32) | m2;
-    const int fitc = S.afit[s];
-    const unsigned long long ofd = S.afd[s], osd = S.asd[s];
-    int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
+    int owner = 0, fh = 0, tw = -1;
     if (win != 0) {
-      const int owner = __ffs(__ballot_sync(0xffffffffu, mine == win)) - 1;
-      int t;
-      if (__shfl_sync(0xffffffffu, (int)from_head, owner)) {
-        // an untracked node wins: it becomes tracked (payload from the candidate buffer)
-        const Cand &cd = a.bufs[owner].cand[s][S.cur[s][owner]];
-        t = nT++;
-        const uint32_t w = key_node(win);
-        if (lane < EGS_G) S.rc[t][lane] = cd.rc[lane]; else if (lane < 2 * EGS_G) S.rm[t][lane - EGS_G] = cd.rm[lane - EGS_G];
-        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = cd.mt; S.dirty[t] = 0; S.fterm[t] = fit_term(w); }
-        {
-          uint8_t st = cd.st[lane];                                // lane == shape index
-          if (st == OPT_NEW && S.observed[lane]) st = OPT_CACHED;
-          S.st[lane][t] = st; S.al[lane][t] = cd.al[lane];
-          S.tkey[lane][t] = (st == OPT_CACHED || st == OPT_NEW) ? cand_key(cd.sc[lane], w) : 0ull;
-          if (st == OPT_ABSENT) S.pmask[lane][t >> 5] |= 1u << (t & 31);
-        }
-        for (int s2 = 0; s2 < ns; s2++)                            // it leaves every untracked list
-          for (int e = lane; e < DK; e += 32) {
-            const unsigned long long q = S.lkey[s2][e];
-            if (q != 0 && key_node(q) == w) S.lkey[s2][e] = 0;
-          }
-        __syncwarp();
-        for (int i = lane; i < ns * D; i += 32) list_head_update(S, i / D, i % D);
-        __syncwarp();
-      } else {
-        t = __shfl_sync(0xffffffffu, best_t, owner);
-      }
-      // Bind: NodeAllocator.Allocate (node.go:87-104) on the tracked copy
-      o_node = S.node[t];
-      const uint32_t masks = S.al[s][t] & S.rq_cmask[s];
-      const unsigned pbit = 1u << (t & 31);
-      int ok = 0;
-      if (lane == 0) {
-        S.st[s][t] = OPT_ABSENT; S.tkey[s][t] = 0; S.pmask[s][t >> 5] |= pbit;    // deferred delete, node.go:90-92
-        S.afit[s] = fitc - 1; S.afd[s] = ofd - S.fterm[t]; S.asd[s] = osd - score_term((uint32_t)o_node, key_score(win));
-        if (single) {                                               // GPUs.Transact gpu.go:164-171
-          const int g = __ffs(masks) - 1;
-          const int c = S.rc[t][g], m = S.rm[t][g], rc = S.rq_core[s], rm = S.rq_mem[s];
-          ok = (c >= rc && m >= rm) ? 1 : 0;
-          if (ok) { S.rc[t][g] = c - rc; S.rm[t][g] = m - rm; }
-        } else {
-          ok = transact_row(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], masks) ? 1 : 0;
-        }
-        S.dirty[t] = 1;
-      }
-      ok = __shfl_sync(0xffffffffu, ok, 0);
-      // Rows changed.  (a) not-yet-observed NEW options of this node are void (only while some shape of the
-      // round is unobserved); (b) UNFIT memos are void -- unless every request of the round is >= 0: rows
-      // then only decrease and an option that did not fit can never fit (exact shortcut).
-      if ((!mono || n_observed < ns) && lane < ns && lane != s) {
-        const uint8_t v = S.st[lane][t];
-        if (v == OPT_UNFIT && !mono) { S.st[lane][t] = OPT_ABSENT; S.pmask[lane][t >> 5] |= pbit; }
-        else if (v == OPT_NEW && !S.observed[lane]) {
-          const unsigned long long k2 = S.tkey[lane][t];
-          S.st[lane][t] = OPT_ABSENT; S.tkey[lane][t] = 0; S.pmask[lane][t >> 5] |= pbit;
-          S.afit[lane] -= 1; S.afd[lane] -= S.fterm[t]; S.asd[lane] -= score_term((uint32_t)o_node, key_score(k2));
-        }
-      }
-      __syncwarp();
-      o_status = ok ? EGS_OK : EGS_ERR_TRANSACT;
-      o_masks = ok ? masks : 0;
+      owner = __ffs(__ballot_sync(0xffffffffu, mine == win)) - 1;
+      fh = __shfl_sync(0xffffffffu, (int)from_head, owner);
+      tw = __shfl_sync(0xffffffffu, best_t, owner);
     }
-    if (lane == 0) {
-      const int r = rel & 31;
-      S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fitc; S.o_fd[r] = ofd; S.o_sd[r] = osd; S.o_alloc[r] = o_masks;
-    }
-    done++;
+    PROF_T(4)
+    commit_pod(S, a, lane, rel, s, win, fh, tw, owner, S.afit[s], S.afd[s], S.asd[s], mono, ns, D, nT, n_observed, PROF_PTR);
+    PROF_T(5) PROF_C(9, 1)
+    p++; done++;
   }
   __syncwarp();
   flush_outputs(S, a.out, a.p0 + flushed, done - flushed, lane);
@@ -536,6 +755,9 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
   }
   if (lane < ns && S.observed[lane]) a.obs_pending[a.set.slot[lane]] = 1;
   if (lane == 0) { a.done[0] = done; a.done[1] = nT; a.done[2] = reason; }
+#ifdef EGS_RESOLVE_PROF
+  if (lane == 0) for (int i = 0; i < 12; i++) atomicAdd((unsigned long long *)a.prof + i, (unsigned long long)prof[i]);
+#endif
 }
 
 // End of a ROUNDS batch: no OPT_NEW may outlive it (the other code paths know three states).
@@ -562,7 +784,7 @@ struct RoundsState {
   uint8_t *d_obs = nullptr; int obs_cap = 0;
   unsigned long long *d_cta_lists = nullptr; AggPart *d_cta_agg = nullptr; int grid = 0;
   ShardBuf *d_bufs = nullptr;       // [RD]; own shard written at index `rank`
-  int32_t *d_done = nullptr; int32_t *h_done = nullptr;
+  int32_t *d_done = nullptr; int32_t *h_done = nullptr; long long *d_prof = nullptr;
   int64_t rounds = 0, pods = 0, tracked = 0; int64_t stops[4] = {0, 0, 0, 0};
 };
 

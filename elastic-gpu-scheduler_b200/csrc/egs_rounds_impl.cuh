@@ -44,7 +44,7 @@ static int rounds_sync_rows(egs_handle *) { return EGS_OK; }   // rows always li
 
 static void rounds_free(RoundsState *r) {
   if (r->comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)r->comm);
-  void *dev[] = {r->d_pod_slot, r->d_obs, r->d_cta_lists, r->d_cta_agg, r->d_bufs, r->d_done};
+  void *dev[] = {r->d_pod_slot, r->d_obs, r->d_cta_lists, r->d_cta_agg, r->d_bufs, r->d_done, r->d_prof};
   for (void *p : dev) if (p) cudaFree(p);
   if (r->h_done) cudaFreeHost(r->h_done);
   *r = RoundsState();
@@ -75,6 +75,8 @@ static int rounds_ensure(egs_handle *h, int P) {
     CK(h, cudaMalloc(&R.d_bufs, sizeof(ShardBuf) * RD));
     CK(h, cudaMemsetAsync(R.d_bufs, 0, sizeof(ShardBuf) * RD, h->stream));
     CK(h, cudaMalloc(&R.d_done, sizeof(int32_t) * 4));
+    CK(h, cudaMalloc(&R.d_prof, sizeof(long long) * 12));
+    CK(h, cudaMemsetAsync(R.d_prof, 0, sizeof(long long) * 12, h->stream));
     CK(h, cudaMallocHost(&R.h_done, sizeof(int32_t) * 4));
     CK(h, cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem)));
   }
@@ -153,7 +155,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
     ma.out = R.d_bufs + h->rank;
     ra.core = h->d_core; ra.mem = h->d_mem; ra.lo = h->lo; ra.hi = h->hi; ra.policy = h->policy; ra.n_shards = h->world;
     ra.set = set; memcpy(ra.reqs, sa.reqs, sizeof ra.reqs); ra.tb = tb; ra.obs_pending = R.d_obs; ra.bufs = R.d_bufs;
-    ra.pod_slot = R.d_pod_slot; ra.p0 = p0; ra.p_limit = plim; ra.out = out; ra.done = R.d_done;
+    ra.pod_slot = R.d_pod_slot; ra.p0 = p0; ra.p_limit = plim; ra.out = out; ra.done = R.d_done; ra.prof = R.d_prof;
 
     if (h->timing) CK(h, cudaEventRecord(ev[0], h->stream));
     k_select<<<grid, SEL_THREADS, 0, h->stream>>>(sa);
