@@ -271,7 +271,8 @@ struct ResolveSmem {                 // shape-major, padded: lanes = tracked slo
   unsigned long long fterm[RT];           // fit_term(node) of each tracked slot
   int rc[RT][EGS_G], rm[RT][EGS_G];
   // per-pod outputs, flushed 32 pods at a time with coalesced stores
-  int o_node[32], o_status[32], o_fit[32]; uint32_t o_alloc[32]; unsigned long long o_fd[32], o_sd[32];
+  int o_node[64], o_status[64], o_fit[64]; uint32_t o_alloc[64]; unsigned long long o_fd[64], o_sd[64];
+  int8_t set_idx[2048];                   // option-table slot id -> index in the round's shape set (-1: not in it)
   Req reqs[RS];
   int hpay_node[RS];                      // node whose payload sits (or is arriving) in hpay[s]; -1 none
   alignas(16) Cand hpay[RS];              // prefetched payload of each shape's best untracked head
@@ -286,15 +287,17 @@ __device__ __forceinline__ void list_head_update(ResolveSmem &S, int s, int d) {
   S.hkey[s][d] = c < len ? S.lkey[s][d * RK + c] : 0ull;
 }
 
-__device__ __forceinline__ void flush_outputs(const ResolveSmem &S, const PodOut &out, int p_first, int n, int lane) {
+// pods [p_first, p_first + n), n <= 32, sit in ring entries (rel0 + i) & 63
+__device__ __forceinline__ void flush_outputs(const ResolveSmem &S, const PodOut &out, int p_first, int rel0, int n, int lane) {
   if (lane < n) {
     const size_t p = (size_t)p_first + lane;
-    if (out.node) out.node[p] = S.o_node[lane];
-    if (out.status) out.status[p] = S.o_status[lane];
-    if (out.fit_count) out.fit_count[p] = S.o_fit[lane];
-    if (out.fit_digest) out.fit_digest[p] = S.o_fd[lane];
-    if (out.score_digest) out.score_digest[p] = S.o_sd[lane];
-    if (out.alloc) reinterpret_cast<uint32_t *>(out.alloc)[p] = S.o_alloc[lane];
+    const int r = (rel0 + lane) & 63;
+    if (out.node) out.node[p] = S.o_node[r];
+    if (out.status) out.status[p] = S.o_status[r];
+    if (out.fit_count) out.fit_count[p] = S.o_fit[r];
+    if (out.fit_digest) out.fit_digest[p] = S.o_fd[r];
+    if (out.score_digest) out.score_digest[p] = S.o_sd[r];
+    if (out.alloc) reinterpret_cast<uint32_t *>(out.alloc)[p] = S.o_alloc[r];
   }
 }
 
@@ -450,7 +453,7 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
     o_masks = ok ? masks : 0;
   }
   if (lane == 0) {
-    const int r = rel & 31;
+    const int r = rel & 63;
     S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fitc; S.o_fd[r] = ofd; S.o_sd[r] = osd; S.o_alloc[r] = o_masks;
   }
 }
@@ -492,8 +495,19 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
   for (int s = 0; s < ns; s++) prefetch_head(S, a, s, D, lane);
   cp_async_commit();
   int nT = 0, done = 0, reason = 0, n_observed = 0, flushed = 0;
-  const int my_set_slot = lane < ns ? a.set.slot[lane] : -1;
-  int myslots = -1;
+  for (int i = lane; i < 2048; i += 32) S.set_idx[i] = -1;
+  __syncwarp();
+  if (lane < ns && a.set.slot[lane] < 2048) S.set_idx[a.set.slot[lane]] = (int8_t)lane;
+  __syncwarp();
+  // pod -> shape index of the round, resolved 32 pods at a time (current block + the next one, so that a
+  // 4-pod window may straddle the block boundary); -1: shape not in the set / past the limit
+  auto load_block = [&](int blk) -> int {
+    const int q = a.p0 + blk * 32 + lane;
+    if (q >= a.p_limit) return -1;
+    const int slot = a.pod_slot[q];
+    return slot < 2048 ? (int)S.set_idx[slot] : -1;
+  };
+  int cur_blk = 0, myshape = load_block(0), nxshape = load_block(1);
   // ---- sequential replay
   int p = a.p0;
 #ifdef EGS_RESOLVE_PROF
@@ -501,26 +515,25 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
 #endif
   while (p < a.p_limit) {
     const int rel = p - a.p0;
-    if ((rel & 31) == 0) {
-      if (rel) { flush_outputs(S, a.out, a.p0 + flushed, 32, lane); flushed += 32; }
-      myslots = (p + lane < a.p_limit) ? a.pod_slot[p + lane] : -1;   // one L2 trip per 32 pods
-    }
+    if ((rel >> 5) != cur_blk) { cur_blk = rel >> 5; myshape = nxshape; nxshape = load_block(cur_blk + 1); }
+    while (rel - flushed >= 32) { flush_outputs(S, a.out, a.p0 + flushed, flushed, 32, lane); flushed += 32; }
+    const int ri = rel & 31;
     // ======== fast path: up to 4 consecutive pods with distinct single-container shapes, decided by four
     // 8-lane groups at once.  Preconditions make the decisions independent of each other's commits except
     // for the hazards checked below; requires rows to be monotone and every shape of the round observed.
-    if (mono && n_observed == ns && nT + 4 <= RT && (rel & 31) <= 28) {
+    if (mono && n_observed == ns && nT + 4 <= RT) {
       int sq[4]; int W = 0;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        const int pslot = __shfl_sync(0xffffffffu, myslots, (rel & 31) + q);
-        const unsigned mb = __ballot_sync(0xffffffffu, my_set_slot == pslot && pslot >= 0);
-        sq[q] = mb ? __ffs(mb) - 1 : -1;
+        const int i = ri + q;
+        const int v0 = __shfl_sync(0xffffffffu, myshape, i & 31), v1 = __shfl_sync(0xffffffffu, nxshape, i & 31);
+        sq[q] = i < 32 ? v0 : v1;
       }
       {
         bool okq = true;
 #pragma unroll
         for (int q = 0; q < 4; q++) {
-          okq = okq && sq[q] >= 0 && p + q < a.p_limit;
+          okq = okq && sq[q] >= 0;
           for (int i = 0; i < q; i++) okq = okq && sq[q] != sq[i];
           if (okq) W = q + 1;
         }
@@ -543,74 +556,125 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
       PROF_T(0)
       if (W >= 2) {
         // ---- decisions (read-only on shared state); groups >= W compute on a valid shape and are ignored
-        {
-          const int rq_c = S.rq_core[sgs], rq_m = S.rq_mem[sgs];
-          const int uu = max(u, 0);
-          // Trade of the one absent option, lane == GPU
-          const int c = S.rc[uu][gl], m = S.rm[uu][gl];
-          const int cmin = (int)seg8_minu((unsigned)c), mmin = (int)seg8_minu((unsigned)m);
-          const int c1 = seg8_max(c), m1 = seg8_max(m);
-          const int c2 = seg8_max(c == c1 ? INT32_MIN : c), m2 = seg8_max(m == m1 ? INT32_MIN : m);
-          const unsigned ceq = (__ballot_sync(0xffffffffu, c == c1) >> (8 * grp)) & 0xFFu;
-          const unsigned meq = (__ballot_sync(0xffffffffu, m == m1) >> (8 * grp)) & 0xFFu;
-          const int cex = (c == c1 && __popc(ceq) == 1) ? c2 : c1, mex = (m == m1 && __popc(meq) == 1) ? m2 : m1;
-          const bool ok = c >= rq_c && m >= rq_m;
-          const int nc = c - rq_c, nm = m - rq_m;
-          const int x = (max(mex, nm) + max(cex, nc)) - (min(mmin, nm) + min(cmin, nc));
-          const int key = (!ok || u < 0) ? -1 : (a.policy == EGS_BINPACK ? (x >> 2) * 8 + gl : gl);
-          const int bk = seg8_max(key);
-          const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
-          const uint32_t nd = (uint32_t)S.node[uu];
-          const unsigned long long tradekey = bk >= 0 ? cand_key(sc, nd) : 0ull;
-          unsigned long long best = 0; int best_t = -1;
-          for (int t = gl; t < nT; t += 8) {                       // the pending slot holds key 0 (zeroed by its bind)
-            const unsigned long long k = S.tkey[sgs][t];
-            if (k > best) { best = k; best_t = t; }
-          }
-          if (tradekey > best) { best = tradekey; best_t = u; }
-          const bool from_head = head > best;
-          const unsigned long long mine = from_head ? head : best;
-          const unsigned long long win = seg8_max64(mine);
-          const unsigned wm = (__ballot_sync(0xffffffffu, mine == win && win != 0) >> (8 * grp)) & 0xFFu;
-          const int ownl = wm ? __ffs(wm) - 1 : 0;                   // lane inside the group
-          const int fh = __shfl_sync(0xffffffffu, (int)from_head, grp * 8 + ownl);
-          const int tw = __shfl_sync(0xffffffffu, best_t, grp * 8 + ownl);
-          if (gl == 0 && grp < W) {
-            PodRec r;
-            r.s = sg; r.u = u; r.bk = bk; r.from_head = fh; r.t = tw; r.d = ownl; r.pad = sc;
-            r.fit = S.afit[sgs] + (bk >= 0); r.fd = S.afd[sgs] + (bk >= 0 ? S.fterm[uu] : 0ull);
-            r.sd = S.asd[sgs] + (bk >= 0 ? score_term(nd, sc) : 0ull); r.win = win;
-            recs[grp] = r;
-          }
+        const int rq_c = S.rq_core[sgs], rq_m = S.rq_mem[sgs];
+        const int uu = max(u, 0);
+        // Trade of the one absent option, lane == GPU
+        const int c = S.rc[uu][gl], m = S.rm[uu][gl];
+        const int cmin = (int)seg8_minu((unsigned)c), mmin = (int)seg8_minu((unsigned)m);
+        const int c1 = seg8_max(c), m1 = seg8_max(m);
+        const int c2 = seg8_max(c == c1 ? INT32_MIN : c), m2 = seg8_max(m == m1 ? INT32_MIN : m);
+        const unsigned ceq = (__ballot_sync(0xffffffffu, c == c1) >> (8 * grp)) & 0xFFu;
+        const unsigned meq = (__ballot_sync(0xffffffffu, m == m1) >> (8 * grp)) & 0xFFu;
+        const int cex = (c == c1 && __popc(ceq) == 1) ? c2 : c1, mex = (m == m1 && __popc(meq) == 1) ? m2 : m1;
+        const bool okt = c >= rq_c && m >= rq_m;
+        const int nc = c - rq_c, nm = m - rq_m;
+        const int x = (max(mex, nm) + max(cex, nc)) - (min(mmin, nm) + min(cmin, nc));
+        const int key = (!okt || u < 0) ? -1 : (a.policy == EGS_BINPACK ? (x >> 2) * 8 + gl : gl);
+        const int bk = seg8_max(key);
+        const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
+        const uint32_t nd = (uint32_t)S.node[uu];
+        const unsigned long long tradekey = bk >= 0 ? cand_key(sc, nd) : 0ull;
+        unsigned long long best = 0; int best_t = -1;
+        for (int t = gl; t < nT; t += 8) {                         // the pending slot holds key 0 (zeroed by its bind)
+          const unsigned long long k = S.tkey[sgs][t];
+          if (k > best) { best = k; best_t = t; }
         }
-        __syncwarp();
+        if (tradekey > best) { best = tradekey; best_t = u; }
+        const bool from_head = head > best;
+        const unsigned long long mine = from_head ? head : best;
+        const unsigned long long win = seg8_max64(mine);
+        const unsigned wm = (__ballot_sync(0xffffffffu, mine == win && win != 0) >> (8 * grp)) & 0xFFu;
+        const int ownl = wm ? __ffs(wm) - 1 : 0;                     // lane inside the group
+        const int fh = __shfl_sync(0xffffffffu, (int)from_head, grp * 8 + ownl);
+        const int tw = __shfl_sync(0xffffffffu, best_t, grp * 8 + ownl);
+        // the shape's aggregates after this pod's filter (group-uniform)
+        const int fit = S.afit[sgs] + (bk >= 0);
+        const unsigned long long fd = S.afd[sgs] + (bk >= 0 ? S.fterm[uu] : 0ull);
+        const unsigned long long sd = S.asd[sgs] + (bk >= 0 ? score_term(nd, sc) : 0ull);
         PROF_T(1)
         // ---- hazards: a head-win changes lists / the tracked set for everyone after it; a pending node
         // that an earlier pod of the group binds must be Traded on the rows AFTER that bind.
+        int hfh[4], ht[4], hu[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          hfh[q] = __shfl_sync(0xffffffffu, (int)(win != 0 && fh), 8 * q);
+          ht[q] = __shfl_sync(0xffffffffu, (win != 0 && !fh) ? tw : -2 - q, 8 * q);
+          hu[q] = __shfl_sync(0xffffffffu, u, 8 * q);
+        }
         int Wc = W;
-        {
-          int hfh[4], ht[4], hu[4];
 #pragma unroll
-          for (int q = 0; q < 4; q++) { hfh[q] = recs[q].win != 0 && recs[q].from_head; ht[q] = recs[q].win != 0 ? recs[q].t : -2; hu[q] = recs[q].u; }
+        for (int j = 3; j >= 1; j--) {
+          bool hz = false;
 #pragma unroll
-          for (int j = 3; j >= 1; j--) {
-            bool hz = false;
+          for (int i = 0; i < j; i++) hz |= hfh[i] || (hu[j] >= 0 && hu[j] == ht[i]);
+          if (hz && j < Wc) Wc = j;
+        }
+        // pods that can commit side by side: tracked wins on pairwise distinct slots (and NOFIT pods);
+        // a head-win (always the last committed pod) goes through the sequential commit
+        int Ws = Wc;
 #pragma unroll
-            for (int i = 0; i < j; i++) hz |= hfh[i] || (hu[j] >= 0 && hu[j] == ht[i]);
-            if (hz && j < Wc) Wc = j;
-          }
+        for (int j = 3; j >= 0; j--) {
+          bool dup = hfh[j];
+#pragma unroll
+          for (int i = 0; i < j; i++) dup |= ht[i] == ht[j];
+          if (dup && j < Ws) Ws = j;
         }
         PROF_T(2)
-        // ---- commits, in pod order
-        for (int q = 0; q < Wc; q++) {
-          const PodRec r = recs[q];
-          if (r.u >= 0 && lane == 0) {                             // this pod's filter Traded slot u
-            if (r.bk >= 0) { S.st[r.s][r.u] = OPT_CACHED; S.al[r.s][r.u] = 1u << (r.bk & 7); S.tkey[r.s][r.u] = cand_key(r.pad, (uint32_t)S.node[r.u]); }
-            else S.st[r.s][r.u] = OPT_UNFIT;
-            S.pmask[r.s][r.u >> 5] &= ~(1u << (r.u & 31));
+        // ---- commits side by side: group leaders write disjoint rows (shape) and slots (node)
+        if (grp < Ws) {
+          int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
+          const unsigned ubit = 1u << (u & 31);
+          if (win != 0) {
+            const int t = tw;
+            const bool same = u == t;                                // the node just Traded wins again (the common case)
+            const uint32_t masks = same ? (1u << (bk & 7)) : (S.al[sgs][t] & 0xFFu);
+            const int g = __ffs(masks) - 1;
+            const int cc = S.rc[t][g], mm = S.rm[t][g];
+            const int ok = (cc >= rq_c && mm >= rq_m) ? 1 : 0;      // GPUs.Transact gpu.go:164-171
+            o_node = S.node[t];
+            const unsigned long long nfd = fd - S.fterm[t], nsd = sd - score_term((uint32_t)o_node, key_score(win));
+            if (gl == 0) {
+              if (u >= 0 && !same) {                                 // this pod's filter Traded slot u
+                if (bk >= 0) { S.st[sgs][u] = OPT_CACHED; S.al[sgs][u] = 1u << (bk & 7); S.tkey[sgs][u] = tradekey; }
+                else S.st[sgs][u] = OPT_UNFIT;
+                S.pmask[sgs][u >> 5] &= ~ubit;
+              }
+              S.st[sgs][t] = OPT_ABSENT; S.tkey[sgs][t] = 0; S.pmask[sgs][t >> 5] |= 1u << (t & 31);   // node.go:90-92
+              S.afit[sgs] = fit - 1; S.afd[sgs] = nfd; S.asd[sgs] = nsd; S.dirty[t] = 1;
+              if (ok) { S.rc[t][g] = cc - rq_c; S.rm[t][g] = mm - rq_m; }
+            }
+            o_status = ok ? EGS_OK : EGS_ERR_TRANSACT;
+            o_masks = ok ? masks : 0;
+          } else if (gl == 0 && u >= 0) {                            // nothing fits; the Trade result still stands
+            if (bk >= 0) { S.st[sgs][u] = OPT_CACHED; S.al[sgs][u] = 1u << (bk & 7); S.tkey[sgs][u] = tradekey; S.afit[sgs] = fit; S.afd[sgs] = fd; S.asd[sgs] = sd; }
+            else S.st[sgs][u] = OPT_UNFIT;
+            S.pmask[sgs][u >> 5] &= ~ubit;
+          }
+          if (gl == 0) {
+            const int r = (rel + grp) & 63;
+            S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fit; S.o_fd[r] = fd; S.o_sd[r] = sd; S.o_alloc[r] = o_masks;
+          }
+        }
+        __syncwarp();
+        // ---- the rest (a head-win, or pods sharing a node) in pod order
+        if (Ws < Wc) {
+          if (gl == 0 && grp >= Ws && grp < Wc) {
+            PodRec r;
+            r.s = sg; r.u = u; r.bk = bk; r.from_head = fh; r.t = tw; r.d = ownl; r.pad = sc;
+            r.fit = fit; r.fd = fd; r.sd = sd; r.win = win;
+            recs[grp] = r;
           }
           __syncwarp();
-          commit_pod(S, a, lane, rel + q, r.s, r.win, r.from_head, r.t, r.d, r.fit, r.fd, r.sd, mono, ns, D, nT, n_observed, PROF_PTR);
+          for (int q = Ws; q < Wc; q++) {
+            const PodRec r = recs[q];
+            if (r.u >= 0 && lane == 0) {                             // this pod's filter Traded slot u
+              if (r.bk >= 0) { S.st[r.s][r.u] = OPT_CACHED; S.al[r.s][r.u] = 1u << (r.bk & 7); S.tkey[r.s][r.u] = cand_key(r.pad, (uint32_t)S.node[r.u]); }
+              else S.st[r.s][r.u] = OPT_UNFIT;
+              S.pmask[r.s][r.u >> 5] &= ~(1u << (r.u & 31));
+            }
+            __syncwarp();
+            commit_pod(S, a, lane, rel + q, r.s, r.win, r.from_head, r.t, r.d, r.fit, r.fd, r.sd, mono, ns, D, nT, n_observed, PROF_PTR);
+          }
         }
         PROF_T(3) PROF_C(6, 1) PROF_C(7, Wc) PROF_C(8, W)
         p += Wc; done += Wc;
@@ -618,10 +682,8 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
       }
     }
     // ======== general path: one pod
-    const int pslot = __shfl_sync(0xffffffffu, myslots, rel & 31);
-    const unsigned mb = __ballot_sync(0xffffffffu, my_set_slot == pslot);
-    if (!mb) { reason = 1; break; }                              // shape outside this round's set
-    const int s = __ffs(mb) - 1;
+    const int s = __shfl_sync(0xffffffffu, myshape, ri);
+    if (s < 0) { reason = 1; break; }                            // shape outside this round's set
     if (nT >= RT) { reason = 2; break; }                          // no free tracked slot for a new winner
     // best untracked candidate per shard (cached heads; consumed entries were skipped when they were zeroed)
     unsigned long long head = 0; bool dry = false;
@@ -722,7 +784,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
     p++; done++;
   }
   __syncwarp();
-  flush_outputs(S, a.out, a.p0 + flushed, done - flushed, lane);
+  while (done > flushed) { const int n = min(32, done - flushed); flush_outputs(S, a.out, a.p0 + flushed, flushed, n, lane); flushed += n; }
   // ---- epilogue: write the tracked nodes back (each shard its own nodes)
   for (int t = 0; t < nT; t++) {
     const int w = S.node[t];
