@@ -27,6 +27,9 @@ struct Shape { int C; egs_unit u[EGS_C]; };
 struct PendingBatch {           // results of a batch whose uid bookkeeping is applied lazily
   int n; uint64_t uid0; std::vector<uint64_t> uids; int32_t *h_node, *h_status; cudaEvent_t done;
 };
+// A finished batch with library-assigned UIDs [uid0, uid0+n): podsMap / podMaps membership is read
+// straight from the result arrays (node.go:150, scheduler.go:224) -- no per-pod hash insert.
+struct AutoBatch { uint64_t uid0; int n; int32_t *h_node, *h_status; bool nodes_valid; };
 
 struct egs_handle {
   int policy = 0, max_nodes = 0, n_pad = 0, g_max = 0, device = 0;
@@ -41,10 +44,15 @@ struct egs_handle {
   uint8_t *d_st = nullptr; int32_t *d_sc = nullptr; uint8_t *d_al = nullptr;
   std::vector<Shape> shapes;
   std::unordered_map<std::string, int> shape_ids;
+  struct ShapeCacheEnt { uint64_t h; int slot; };
+  std::vector<ShapeCacheEnt> shape_cache = std::vector<ShapeCacheEnt>(1024, ShapeCacheEnt{0, -1});   // open addressing
   // reference bookkeeping that never reaches the device
   std::unordered_set<NodeUid, NodeUidHash> pods_map;           // NodeAllocator.podsMap (node.go:16)
   std::unordered_set<uint64_t> pod_maps, released;             // BaseScheduler.podMaps / releasedPodMap
   std::vector<PendingBatch> pending;
+  std::vector<AutoBatch> auto_batches;
+  std::unordered_set<uint64_t> auto_gone_pod;                  // auto uids erased from podMaps (ForgetPod)
+  std::unordered_set<NodeUid, NodeUidHash> auto_gone_node;     // auto (node, uid) erased from a podsMap
   uint64_t next_uid = 0x8000000000000000ull;
   // scratch
   Partial *d_partials = nullptr; unsigned int *d_ticket = nullptr; int32_t *d_result = nullptr;
@@ -126,7 +134,41 @@ static int check_units(int C, const egs_unit *u) {
 
 // request -> option-table slot.  The reference keys its cache on sha256(String())[0:8]
 // (allocate.go:30-33); the unit tuple is the same key up to a 32-bit prefix collision.
-static int intern(egs_handle *h, int C, const egs_unit *u, int *slot) {
+static inline uint64_t shape_hash(int C, const egs_unit *u) {
+  uint64_t x = 0x9E3779B97F4A7C15ull * (uint64_t)C;
+  for (int i = 0; i < C; i++) {
+    x = mix64(x ^ (((uint64_t)(uint32_t)u[i].core << 32) | (uint32_t)u[i].mem));
+    x ^= (uint64_t)(uint32_t)u[i].count * 0xD6E8FEB86659FD93ull;
+  }
+  return x | 1;
+}
+
+static int intern_slow(egs_handle *h, int C, const egs_unit *u, int *slot);
+
+// hot entry: one hash + one probe per pod (a batch of 10^6 pods re-uses a handful of shapes)
+static inline int intern(egs_handle *h, int C, const egs_unit *u, int *slot) {
+  if (C >= 1 && C <= EGS_C && u) {
+    const uint64_t hv = shape_hash(C, u);
+    const size_t mask = h->shape_cache.size() - 1;
+    for (size_t i = hv & mask, n = 0; n < 8; i = (i + 1) & mask, n++) {
+      const auto &e = h->shape_cache[i];
+      if (e.slot < 0) break;
+      if (e.h == hv) {
+        const Shape &sh = h->shapes[e.slot];
+        if (sh.C == C && memcmp(sh.u, u, sizeof(egs_unit) * C) == 0) { *slot = e.slot; return EGS_OK; }
+      }
+    }
+  }
+  TRY(intern_slow(h, C, u, slot));
+  if (h->shapes.size() * 4 > h->shape_cache.size()) h->shape_cache.assign(h->shape_cache.size() * 4, egs_handle::ShapeCacheEnt{0, -1});
+  const uint64_t hv = shape_hash(C, u);
+  const size_t mask = h->shape_cache.size() - 1;
+  for (size_t i = hv & mask, n = 0; n < 8; i = (i + 1) & mask, n++)
+    if (h->shape_cache[i].slot < 0) { h->shape_cache[i] = egs_handle::ShapeCacheEnt{hv, *slot}; break; }
+  return EGS_OK;
+}
+
+static int intern_slow(egs_handle *h, int C, const egs_unit *u, int *slot) {
   TRY(check_units(C, u));
   std::string key((const char *)&C, sizeof C);
   key.append((const char *)u, sizeof(egs_unit) * C);
@@ -149,9 +191,33 @@ static Req make_req(int C, const egs_unit *u) {
 }
 static bool is_single(int C, const egs_unit *u) { return C == 1 && u[0].count == 0 && u[0].core >= 0 && u[0].mem >= 0; }
 
+static const AutoBatch *auto_find(const egs_handle *h, uint64_t uid) {
+  for (const auto &b : h->auto_batches) if (uid >= b.uid0 && uid < b.uid0 + (uint64_t)b.n) return &b;
+  return nullptr;
+}
+static bool in_pods_map(const egs_handle *h, int node, uint64_t uid) {
+  if (h->pods_map.count(NodeUid{node, uid})) return true;
+  const AutoBatch *b = auto_find(h, uid);
+  return b && b->nodes_valid && b->h_node[uid - b->uid0] == node && !h->auto_gone_node.count(NodeUid{node, uid});
+}
+static bool in_pod_maps(const egs_handle *h, uint64_t uid) {
+  if (h->pod_maps.count(uid)) return true;
+  const AutoBatch *b = auto_find(h, uid);
+  return b && b->h_node[uid - b->uid0] >= 0 && b->h_status[uid - b->uid0] == EGS_OK && !h->auto_gone_pod.count(uid);
+}
+static void free_auto_batches(egs_handle *h) {
+  for (auto &b : h->auto_batches) { cudaFreeHost(b.h_node); cudaFreeHost(b.h_status); }
+  h->auto_batches.clear(); h->auto_gone_pod.clear(); h->auto_gone_node.clear();
+}
+
 static int flush_pending(egs_handle *h) {
   for (auto &b : h->pending) {
     CK(h, cudaEventSynchronize(b.done));
+    if (b.uids.empty()) {                                        // library-assigned contiguous uids: keep the arrays
+      h->auto_batches.push_back(AutoBatch{b.uid0, b.n, b.h_node, b.h_status, true});
+      cudaEventDestroy(b.done);
+      continue;
+    }
     for (int p = 0; p < b.n; p++) {
       uint64_t uid = b.uids.empty() ? b.uid0 + (uint64_t)p : b.uids[p];
       if (b.h_node[p] >= 0) {
@@ -214,6 +280,7 @@ extern "C" int egs_destroy(egs_handle *h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   flush_pending(h);
+  free_auto_batches(h);
   rounds_free(&h->rounds);
   void *dev[] = {h->d_core, h->d_mem, h->d_mem_total, h->d_st, h->d_sc, h->d_al, h->d_partials, h->d_ticket, h->d_snap_core, h->d_snap_mem, h->d_snap_total,
                  h->d_result, h->d_ids, h->d_fit, h->d_score, h->d_ev_fit, h->d_ev_score, h->d_ev_gpu, h->d_flush,
@@ -304,7 +371,21 @@ static int load_rows(egs_handle *h, int node0, int n, int gpu_count, int mem_tot
 // podsMap entries of nodes [node0, node0+n) vanish with their NodeAllocator (one pass)
 static void drop_node_pods(egs_handle *h, int node0, int n) {
   if (h->pods_map.empty()) return;
-  if (node0 == 0 && n >= h->max_nodes) { h->pods_map.clear(); return; }
+  if (node0 == 0 && n >= h->max_nodes) {
+    h->pods_map.clear();
+    // auto batches: every node reloaded -> no podsMap entry survives; podMaps (scheduler level) does
+    for (auto &b : h->auto_batches) b.nodes_valid = false;
+    h->auto_gone_node.clear();
+    return;
+  }
+  // partial reload: materialise the auto batches into the hash sets first (rare path)
+  for (auto &b : h->auto_batches)
+    for (int p = 0; p < b.n; p++) if (b.h_node[p] >= 0) {
+      const uint64_t uid = b.uid0 + p;
+      if (b.nodes_valid && !h->auto_gone_node.count(NodeUid{b.h_node[p], uid})) h->pods_map.insert(NodeUid{b.h_node[p], uid});
+      if (b.h_status[p] == EGS_OK && !h->auto_gone_pod.count(uid)) h->pod_maps.insert(uid);
+    }
+  free_auto_batches(h);
   for (auto it = h->pods_map.begin(); it != h->pods_map.end();)
     if (it->node >= node0 && it->node < node0 + n) it = h->pods_map.erase(it); else ++it;
 }
@@ -408,7 +489,7 @@ extern "C" int egs_state_restore(egs_handle *h) {
   if (!h->shapes.empty())
     CK(h, cudaMemsetAsync(h->d_st, OPT_ABSENT, (size_t)h->n_pad * h->shapes.size(), h->stream));
   h->h_gpu_count = h->snap_gpu_count; h->h_mem_total = h->snap_mem_total;
-  h->pods_map.clear(); h->pod_maps.clear(); h->released.clear();
+  h->pods_map.clear(); h->pod_maps.clear(); h->released.clear(); free_auto_batches(h);
   h->rounds.index_valid = false;
   return EGS_OK;
 }
@@ -492,7 +573,7 @@ static int bind_or_peek(egs_handle *h, int consume, int node_id, int C, const eg
   a.core = h->d_core; a.mem = h->d_mem; a.mem_total = h->d_mem_total; a.node = node_id;
   a.req = make_req(C, units); a.t = table(h, slot);
   a.all_st = h->d_st; a.slot_stride = (size_t)h->n_pad; a.n_slots = (int)h->shapes.size();
-  const bool known = consume && h->pods_map.count(NodeUid{node_id, uid}) > 0;
+  const bool known = consume && in_pods_map(h, node_id, uid);
   a.skip_transact = known ? 1 : 0; a.consume = consume; a.result = h->d_result;
   k_bind<<<1, 1, 0, h->stream>>>(a);
   CK(h, cudaGetLastError());
@@ -562,8 +643,8 @@ extern "C" int egs_pod_apply(egs_handle *h, int node_id, int n_containers, const
   if (h->h_gpu_count[node_id] == 0) return EGS_ERR_NO_NODE;
   TRY(check_units(n_containers, units));
   TRY(flush_pending(h));
-  if (h->pod_maps.count(uid)) return EGS_OK;                                // scheduler.go:239-241
-  if (!h->pods_map.count(NodeUid{node_id, uid})) {                          // node.go:149
+  if (in_pod_maps(h, uid)) return EGS_OK;                                   // scheduler.go:239-241
+  if (!in_pods_map(h, node_id, uid)) {                                      // node.go:149
     TRY(apply_lists(h, 0, node_id, n_containers, units, alloc_off, alloc_idx));
     h->pods_map.insert(NodeUid{node_id, uid});
   }
@@ -580,7 +661,7 @@ extern "C" int egs_node_replay_pod(egs_handle *h, int node_id, int n_containers,
   if (h->h_gpu_count[node_id] == 0) return EGS_ERR_NO_NODE;
   TRY(check_units(n_containers, units));
   TRY(flush_pending(h));
-  if (!h->pods_map.count(NodeUid{node_id, uid})) {
+  if (!in_pods_map(h, node_id, uid)) {
     TRY(apply_lists(h, 0, node_id, n_containers, units, alloc_off, alloc_idx));
     h->pods_map.insert(NodeUid{node_id, uid});
   }
@@ -597,13 +678,15 @@ extern "C" int egs_pod_cancel(egs_handle *h, int node_id, int n_containers, cons
     if (node_id >= h->max_nodes) return EGS_ERR_BAD_ARG;
     if (h->h_gpu_count[node_id] == 0) return EGS_ERR_NO_NODE;
     TRY(check_units(n_containers, units));
-    auto it = h->pods_map.find(NodeUid{node_id, uid});
-    if (it != h->pods_map.end()) {                                          // node.go:131
+    if (in_pods_map(h, node_id, uid)) {                                     // node.go:131
       TRY(apply_lists(h, 1, node_id, n_containers, units, alloc_off, alloc_idx));
-      h->pods_map.erase(it);
+      if (!h->pods_map.erase(NodeUid{node_id, uid})) h->auto_gone_node.insert(NodeUid{node_id, uid});
     }
   }
-  if (h->pod_maps.erase(uid)) h->released.insert(uid);                      // scheduler.go:261-264
+  if (in_pod_maps(h, uid)) {                                                // scheduler.go:261-264
+    if (!h->pod_maps.erase(uid)) h->auto_gone_pod.insert(uid);
+    h->released.insert(uid);
+  }
   return EGS_OK;
 }
 
@@ -611,7 +694,7 @@ extern "C" int egs_pod_known(egs_handle *h, uint64_t uid) {
   if (!h) return 0;
   Guard g(h);
   if (flush_pending(h) != EGS_OK) return 0;
-  return h->pod_maps.count(uid) ? 1 : 0;
+  return in_pod_maps(h, uid) ? 1 : 0;
 }
 extern "C" int egs_pod_released(egs_handle *h, uint64_t uid) {
   if (!h) return 0;
@@ -675,7 +758,7 @@ static int batch_common(egs_handle *h, int mode, int P, const int32_t *c_off, co
     TRY(flush_pending(h));
     std::unordered_set<uint64_t> seen; seen.reserve((size_t)P * 2);
     for (int p = 0; p < P; p++) {
-      if (!seen.insert(uids[p]).second || h->pod_maps.count(uids[p])) return fail(h, EGS_ERR_BAD_ARG, "duplicate or known uid");
+      if (!seen.insert(uids[p]).second || in_pod_maps(h, uids[p])) return fail(h, EGS_ERR_BAD_ARG, "duplicate or known uid");
     }
   }
   PodOut dev = out;

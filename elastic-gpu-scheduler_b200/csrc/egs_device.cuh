@@ -34,8 +34,13 @@ __host__ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
   return z ^ (z >> 31);
 }
 __host__ __device__ __forceinline__ uint64_t fit_term(uint32_t node) { return mix64(2ull * node + 1ull); }
+// score digest term = h2(node) * (2*score + 1): h2 is per node, so it is hashed once and reused for every shape
+__host__ __device__ __forceinline__ uint64_t score_base(uint32_t node) { return mix64(2ull * node + 2ull); }
+__host__ __device__ __forceinline__ uint64_t score_term_b(uint64_t base, int32_t score) {
+  return base * (2ull * (uint64_t)(uint32_t)score + 1ull);
+}
 __host__ __device__ __forceinline__ uint64_t score_term(uint32_t node, int32_t score) {
-  return mix64((((uint64_t)node << 32) | (uint32_t)score) ^ 0xA5A5A5A5A5A5A5A5ull);
+  return score_term_b(score_base(node), score);
 }
 // candidate ordering: higher score first, then lower node id ("first max in list order").
 // Scores are >= 0 (rater.go:49-50 with operands >= 0), so key 0 means "no candidate".

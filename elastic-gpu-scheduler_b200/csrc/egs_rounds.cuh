@@ -87,6 +87,32 @@ __device__ __forceinline__ void list_merge(unsigned long long &L, unsigned long 
   }
 }
 
+// 32 keys, one per lane -> sorted descending across the lanes (bitonic network, 15 exchange steps)
+__device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+      const bool take_max = ((lane & j) == 0) == ((lane & k) == 0);
+      v = take_max ? (o > v ? o : v) : (o < v ? o : v);
+    }
+  }
+  return v;
+}
+// two descending lists (one key per lane each) -> the 32 largest of their union, descending:
+// max(a[i], b[31-i]) is a bitonic sequence holding exactly those keys; 5 merge steps sort it
+__device__ __forceinline__ unsigned long long merge_top32(unsigned long long a, unsigned long long b, int lane) {
+  const unsigned long long br = __shfl_sync(0xffffffffu, b, 31 - lane);
+  unsigned long long v = a > br ? a : br;
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v, j);
+    v = ((lane & j) == 0) ? (o > v ? o : v) : (o < v ? o : v);
+  }
+  return v;
+}
+
 // --------------------------------------------------------------------------------------------
 // k_select
 // --------------------------------------------------------------------------------------------
@@ -102,9 +128,13 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
   for (int s = lane; s < RS; s += 32) { s_agg[warp][s].fd = 0; s_agg[warp][s].sd = 0; s_agg[warp][s].fit = 0; }
   for (int i = lane; i < RS * RK; i += 32) (&s_list[warp][0][0])[i] = 0;
   __syncwarp();
+  static_assert(RK == 32, "top-K lists are one key per lane");
   const int n_chunks = (a.hi - a.lo + 127) / 128;
   for (int chunk = gwarp; chunk < n_chunks; chunk += nwarps) {
-    const int base = a.lo + chunk * 128 + lane * 4;           // 4 consecutive nodes per lane
+    const int base = a.lo + chunk * 128 + lane;               // lane handles nodes base + 32*j: tied scores arrive in key order
+    unsigned long long h1[4], h2[4];                          // per-node digest hashes, shared by all shapes
+#pragma unroll
+    for (int j = 0; j < 4; j++) { h1[j] = fit_term((uint32_t)(base + 32 * j)); h2[j] = score_base((uint32_t)(base + 32 * j)); }
     for (int s = 0; s < a.set.n; s++) {
       const int slot = s_slot[s];
       uint8_t *stp = tb_st(a.tb, slot);
@@ -113,23 +143,22 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
       const bool pending = a.obs_pending[slot] != 0;
       const Req &r = s_reqs[s];
       const bool single = req_is_single(r);
-      uchar4 st4 = make_uchar4(OPT_UNFIT, OPT_UNFIT, OPT_UNFIT, OPT_UNFIT);
-      int4 sc4 = make_int4(0, 0, 0, 0);
-      if (base < a.hi) {                                       // n_pad is a multiple of 1024: in-bounds vector loads
-        st4 = *reinterpret_cast<const uchar4 *>(stp + base);
-        sc4 = *reinterpret_cast<const int4 *>(scp + base);
+      uint8_t st[4]; int sc[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int i = base + 32 * j;
+        st[j] = i < a.hi ? stp[i] : (uint8_t)OPT_UNFIT;
+        sc[j] = i < a.hi ? scp[i] : 0;
       }
-      uint8_t st[4] = {st4.x, st4.y, st4.z, st4.w};
-      int sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
-      bool dirty = false;
       unsigned long long key[4], fd = 0, sd = 0;
       int fit = 0;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
-        const int i = base + j;
+        const int i = base + 32 * j;
         key[j] = 0;
         if (i >= a.hi) continue;
-        if (st[j] == OPT_NEW && pending) { st[j] = OPT_CACHED; dirty = true; }
+        const uint8_t st0 = st[j];
+        if (st[j] == OPT_NEW && pending) st[j] = OPT_CACHED;
         if (st[j] == OPT_ABSENT) {                             // full evaluate (gpu.go:65-129)
           int c[EGS_G], m[EGS_G]; uint32_t masks;
           load_row(a.core, a.mem, (size_t)i, c, m);
@@ -140,33 +169,32 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
           } else {
             st[j] = OPT_UNFIT;
           }
-          dirty = true;
         }
+        if (st[j] != st0) stp[i] = st[j];
         if (st[j] == OPT_CACHED || st[j] == OPT_NEW) {
           key[j] = cand_key(sc[j], (uint32_t)i);
-          fit++; fd += fit_term((uint32_t)i); sd += score_term((uint32_t)i, sc[j]);
+          fit++; fd += h1[j]; sd += score_term_b(h2[j], sc[j]);
         }
       }
-      if (dirty && base < a.hi) *reinterpret_cast<uchar4 *>(stp + base) = make_uchar4(st[0], st[1], st[2], st[3]);
       fit = warp_sum_i32(fit); fd = warp_sum_u64(fd); sd = warp_sum_u64(sd);
       if (lane == 0) { s_agg[warp][s].fit += fit; s_agg[warp][s].fd += fd; s_agg[warp][s].sd += sd; }
-      // top-RK of this warp for shape s
-      unsigned long long L = lane < RK ? s_list[warp][s][lane] : 0ull;
+      // top-32 of this warp for shape s: sort 32 keys, merge sorted lists
+      unsigned long long L = s_list[warp][s][lane];
       bool changed = false;
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const unsigned long long kth = __shfl_sync(0xffffffffu, L, RK - 1);
-        if (__ballot_sync(0xffffffffu, key[j] > kth)) { list_merge(L, key[j], lane); changed = true; }
+        if (__ballot_sync(0xffffffffu, key[j] > kth)) { L = merge_top32(L, warp_sort_desc(key[j], lane), lane); changed = true; }
       }
-      if (changed && lane < RK) s_list[warp][s][lane] = L;
+      if (changed) s_list[warp][s][lane] = L;
       __syncwarp();
     }
   }
   __syncthreads();
   // fold the warps of this CTA: warp w owns shapes s == w (mod SEL_WARPS)
   for (int s = warp; s < a.set.n; s += SEL_WARPS) {
-    unsigned long long L = lane < RK ? s_list[0][s][lane] : 0ull;
-    for (int w = 1; w < SEL_WARPS; w++) list_merge(L, lane < RK ? s_list[w][s][lane] : 0ull, lane);
+    unsigned long long L = s_list[0][s][lane];
+    for (int w = 1; w < SEL_WARPS; w++) L = merge_top32(L, s_list[w][s][lane], lane);
     if (lane < RK) a.cta_lists[((size_t)blockIdx.x * RS + s) * RK + lane] = L;
     if (lane == 0) {
       AggPart t; t.fd = 0; t.sd = 0; t.fit = 0; t.pad = 0;
@@ -196,15 +224,15 @@ __global__ void __launch_bounds__(256) k_merge(MergeArgs a) {
   unsigned long long L = 0;
   AggPart ag; ag.fd = 0; ag.sd = 0; ag.fit = 0; ag.pad = 0;
   for (int c = warp; c < a.n_cta; c += 8) {
-    list_merge(L, lane < RK ? a.cta_lists[((size_t)c * RS + s) * RK + lane] : 0ull, lane);
+    L = merge_top32(L, a.cta_lists[((size_t)c * RS + s) * RK + lane], lane);
     if (lane == 0) { const AggPart p = a.cta_agg[(size_t)c * RS + s]; ag.fd += p.fd; ag.sd += p.sd; ag.fit += p.fit; }
   }
   if (lane < RK) s_l[warp][lane] = L;
   if (lane == 0) s_a[warp] = ag;
   __syncthreads();
   if (warp == 0) {
-    L = lane < RK ? s_l[0][lane] : 0ull;
-    for (int w = 1; w < 8; w++) list_merge(L, lane < RK ? s_l[w][lane] : 0ull, lane);
+    L = s_l[0][lane];
+    for (int w = 1; w < 8; w++) L = merge_top32(L, s_l[w][lane], lane);
     if (lane < RK) s_final[lane] = L;
     if (lane == 0) {
       AggPart t = s_a[0];
@@ -269,22 +297,38 @@ struct ResolveSmem {                 // shape-major, padded: lanes = tracked slo
   int rq_single[RS], rq_core[RS], rq_mem[RS]; uint32_t rq_cmask[RS];
   int node[RT], mt[RT], dirty[RT];
   unsigned long long fterm[RT];           // fit_term(node) of each tracked slot
+  unsigned long long sbase[RT];           // score_base(node) of each tracked slot
   int rc[RT][EGS_G], rm[RT][EGS_G];
   // per-pod outputs, flushed 32 pods at a time with coalesced stores
   int o_node[64], o_status[64], o_fit[64]; uint32_t o_alloc[64]; unsigned long long o_fd[64], o_sd[64];
   int8_t set_idx[2048];                   // option-table slot id -> index in the round's shape set (-1: not in it)
   Req reqs[RS];
+  int hset[512];                          // open-addressed set of tracked node ids (-1 empty): lazy list maintenance
   int hpay_node[RS];                      // node whose payload sits (or is arriving) in hpay[s]; -1 none
   alignas(16) Cand hpay[RS];              // prefetched payload of each shape's best untracked head
 };
 
-// advance list (s, d) past consumed entries and cache its head
+__device__ __forceinline__ unsigned hset_slot(uint32_t node) { return (node * 2654435761u) >> 23; }   // 9 bits
+__device__ __forceinline__ bool hset_has(const ResolveSmem &S, uint32_t node) {
+  for (unsigned i = hset_slot(node);; i = (i + 1) & 511u) {
+    const int v = S.hset[i];
+    if (v == (int)node) return true;
+    if (v < 0) return false;
+  }
+}
+__device__ __forceinline__ void hset_add(ResolveSmem &S, uint32_t node) {   // one lane; at most RT (256) entries
+  unsigned i = hset_slot(node);
+  while (S.hset[i] >= 0) i = (i + 1) & 511u;
+  S.hset[i] = (int)node;
+}
+// advance list (s, d) past entries whose node is tracked by now, and cache its head
 __device__ __forceinline__ void list_head_update(ResolveSmem &S, int s, int d) {
   int c = S.cur[s][d];
   const int len = S.len[s][d];
-  while (c < len && S.lkey[s][d * RK + c] == 0) c++;
+  unsigned long long k = 0;
+  while (c < len) { k = S.lkey[s][d * RK + c]; if (!hset_has(S, key_node(k))) break; c++; }
   S.cur[s][d] = c;
-  S.hkey[s][d] = c < len ? S.lkey[s][d * RK + c] : 0ull;
+  S.hkey[s][d] = c < len ? k : 0ull;
 }
 
 // pods [p_first, p_first + n), n <= 32, sit in ring entries (rel0 + i) & 63
@@ -377,31 +421,31 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
       const uint32_t w = key_node(win);
       cp_async_wait_all();
       __syncwarp();
-      const bool pre = S.hpay_node[s] == (int)w;
-      const Cand &cd = pre ? S.hpay[s] : a.bufs[d].cand[s][S.cur[s][d]];
       {
-        const int rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0;      // rc[8] and rm[8] are contiguous
-        const int mtv = cd.mt;
-        uint8_t st = cd.st[lane];                                // lane == shape index
-        const int scv = cd.sc[lane]; const uint32_t alv = cd.al[lane];
-        if (lane < EGS_G) S.rc[t][lane] = rowv; else if (lane < 2 * EGS_G) S.rm[t][lane - EGS_G] = rowv;
-        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = mtv; S.dirty[t] = 0; S.fterm[t] = fit_term(w); }
-        if (st == OPT_NEW && S.observed[lane]) st = OPT_CACHED;
+        int rowv, mtv, scv; uint32_t alv; uint8_t st;
+        if (S.hpay_node[s] == (int)w) {                            // warp-uniform: payload already in shared memory
+          const Cand &cd = S.hpay[s];
+          rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0; mtv = cd.mt; st = cd.st[lane]; scv = cd.sc[lane]; alv = cd.al[lane];
+        } else {
+          const Cand &cd = a.bufs[d].cand[s][S.cur[s][d]];
+          rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0; mtv = cd.mt; st = cd.st[lane]; scv = cd.sc[lane]; alv = cd.al[lane];
+        }
+        if (lane < EGS_G) S.rc[t][lane] = rowv; else if (lane < 2 * EGS_G) S.rm[t][lane - EGS_G] = rowv;   // rc[8], rm[8] contiguous
+        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = mtv; S.dirty[t] = 0; S.fterm[t] = fit_term(w); S.sbase[t] = score_base(w); hset_add(S, w); }
+        if (st == OPT_NEW && S.observed[lane]) st = OPT_CACHED;   // lane == shape index
         S.st[lane][t] = st; S.al[lane][t] = alv;
         S.tkey[lane][t] = (st == OPT_CACHED || st == OPT_NEW) ? cand_key(scv, w) : 0ull;
         if (st == OPT_ABSENT) S.pmask[lane][t >> 5] |= 1u << (t & 31);
       }
-      for (int e = lane; e < DK; e += 32) {                       // it leaves every untracked list
-#pragma unroll 4
-        for (int s2 = 0; s2 < ns; s2++) {
-          const unsigned long long q = S.lkey[s2][e];
-          if (q != 0 && key_node(q) == w) S.lkey[s2][e] = 0;
-        }
+      __syncwarp();
+      // it leaves the untracked lists lazily: only lists whose HEAD is this node advance now (entries deeper
+      // in a list are skipped when they surface); then the changed heads get their payloads prefetched
+      for (int i = lane; i < ns * D; i += 32) {
+        const unsigned long long hk = S.hkey[i / D][i % D];
+        if (hk != 0 && key_node(hk) == w) list_head_update(S, i / D, i % D);
       }
       __syncwarp();
-      for (int i = lane; i < ns * D; i += 32) list_head_update(S, i / D, i % D);
-      __syncwarp();
-      {                                                            // heads that changed: prefetch their payloads
+      {
         bool need = false;
         if (lane < ns) { int dd; const unsigned long long k = best_head(S, lane, D, dd); need = (k ? (int)key_node(k) : -1) != S.hpay_node[lane]; }
         for (unsigned rem = __ballot_sync(0xffffffffu, need); rem; rem &= rem - 1) prefetch_head(S, a, __ffs(rem) - 1, D, lane);
@@ -417,7 +461,7 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
     // deferred delete of the option (node.go:90-92) + aggregates: computed by every lane (broadcast loads),
     // stored by lane 0 -- no divergent region on the common single-container path
     const int nfit = fitc - 1;
-    const unsigned long long nfd = ofd - S.fterm[t], nsd = osd - score_term((uint32_t)o_node, key_score(win));
+    const unsigned long long nfd = ofd - S.fterm[t], nsd = osd - score_term_b(S.sbase[t], key_score(win));
     const unsigned npm = S.pmask[s][t >> 5] | pbit;
     if (single) {                                                 // GPUs.Transact gpu.go:164-171
       const int g = __ffs(masks) - 1;
@@ -445,7 +489,7 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
       else if (v == OPT_NEW && !S.observed[lane]) {
         const unsigned long long k2 = S.tkey[lane][t];
         S.st[lane][t] = OPT_ABSENT; S.tkey[lane][t] = 0; S.pmask[lane][t >> 5] |= pbit;
-        S.afit[lane] -= 1; S.afd[lane] -= S.fterm[t]; S.asd[lane] -= score_term((uint32_t)o_node, key_score(k2));
+        S.afit[lane] -= 1; S.afd[lane] -= S.fterm[t]; S.asd[lane] -= score_term_b(S.sbase[t], key_score(k2));
       }
     }
     __syncwarp();
@@ -467,6 +511,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
   const int grp = lane >> 3, gl = lane & 7;                      // 8-lane groups: one lane per GPU of a node
   const unsigned gmask = 0xFFu << (8 * grp);
   // ---- prologue
+  for (int i = lane; i < 512; i += 32) S.hset[i] = -1;
   bool mono = true;                                              // all requests >= 0: rows only decrease in this round
   {
     const int s = lane;                                          // RS == 32: one shape per lane
@@ -590,7 +635,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
         // the shape's aggregates after this pod's filter (group-uniform)
         const int fit = S.afit[sgs] + (bk >= 0);
         const unsigned long long fd = S.afd[sgs] + (bk >= 0 ? S.fterm[uu] : 0ull);
-        const unsigned long long sd = S.asd[sgs] + (bk >= 0 ? score_term(nd, sc) : 0ull);
+        const unsigned long long sd = S.asd[sgs] + (bk >= 0 ? score_term_b(S.sbase[uu], sc) : 0ull);
         PROF_T(1)
         // ---- hazards: a head-win changes lists / the tracked set for everyone after it; a pending node
         // that an earlier pod of the group binds must be Traded on the rows AFTER that bind.
@@ -632,7 +677,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
             const int cc = S.rc[t][g], mm = S.rm[t][g];
             const int ok = (cc >= rq_c && mm >= rq_m) ? 1 : 0;      // GPUs.Transact gpu.go:164-171
             o_node = S.node[t];
-            const unsigned long long nfd = fd - S.fterm[t], nsd = sd - score_term((uint32_t)o_node, key_score(win));
+            const unsigned long long nfd = fd - S.fterm[t], nsd = sd - score_term_b(S.sbase[t], key_score(win));
             if (gl == 0) {
               if (u >= 0 && !same) {                                 // this pod's filter Traded slot u
                 if (bk >= 0) { S.st[sgs][u] = OPT_CACHED; S.al[sgs][u] = 1u << (bk & 7); S.tkey[sgs][u] = tradekey; }
@@ -739,7 +784,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
               }
             }
             for (unsigned rem = __ballot_sync(0xffffffffu, okl); rem; rem &= rem - 1) {   // usually one leader
-              if (lane == __ffs(rem) - 1) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term((uint32_t)S.node[t], sc); }
+              if (lane == __ffs(rem) - 1) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term_b(S.sbase[t], sc); }
               __syncwarp();
             }
           }
@@ -753,7 +798,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
             else S.st[s][t] = OPT_UNFIT;
           }
           for (unsigned rem = word; rem; rem &= rem - 1) {
-            if (lane == __ffs(rem) - 1 && ok) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term((uint32_t)S.node[t], sc); }
+            if (lane == __ffs(rem) - 1 && ok) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term_b(S.sbase[t], sc); }
             __syncwarp();
           }
         }

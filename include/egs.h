@@ -145,7 +145,7 @@ int egs_pod_released(egs_handle *h, uint64_t uid);   /* 1 / 0, scheduler.go:276-
  *   out_alloc_mask[p*EGS_MAX_CONTAINERS + c]
  *   out_fit_count[p]   number of fit nodes
  *   out_fit_digest[p]  sum over fit nodes of egs_mix64(2*node+1)                       (mod 2^64)
- *   out_score_digest[p] sum over fit nodes of egs_mix64(((u64)node<<32 | (u32)score) ^ 0xA5A5A5A5A5A5A5A5)
+ *   out_score_digest[p] sum over fit nodes of egs_mix64(2*node+2) * (2*(u64)(u32)score + 1)             (mod 2^64)
  * The digests are sums so that node shards compose by addition.
  */
 enum egs_batch_mode {

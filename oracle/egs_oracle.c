@@ -572,7 +572,7 @@ int egso_schedule_batch(egso *o, int P, const int32_t *c_off, const egso_unit *u
     int w = -1; int64_t best = 0;
     for (int j = 0; j < nf; j++) {
       fd += egso_mix64(2ull * (uint64_t)ids[j] + 1);
-      sd += egso_mix64((((uint64_t)ids[j] << 32) | (uint32_t)(int32_t)sc[j]) ^ 0xA5A5A5A5A5A5A5A5ull);
+      sd += egso_mix64(2ull * (uint64_t)ids[j] + 2) * (2ull * (uint64_t)(uint32_t)(int32_t)sc[j] + 1);
       if (w < 0 || sc[j] > best) { w = ids[j]; best = sc[j]; }   /* first max */
     }
     if (p < vec_pods) {

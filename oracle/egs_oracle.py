@@ -329,7 +329,7 @@ def fit_digest_term(node: int) -> int:
 
 
 def score_digest_term(node: int, score: int) -> int:
-    return mix64(((node << 32) | (score & 0xFFFFFFFF)) ^ 0xA5A5A5A5A5A5A5A5)
+    return (mix64(2 * node + 2) * (2 * (score & 0xFFFFFFFF) + 1)) & MASK64
 
 
 class Scheduler:

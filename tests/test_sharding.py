@@ -46,7 +46,7 @@ def _gloo_worker(rank, world, port, q):
         _, sc = o.score(ids[fit.astype(bool)], req)
         L = oracle_c.lib()
         fd = sum(L.egso_mix64(2 * int(i) + 1) for i in ids[fit.astype(bool)]) & (2**64 - 1)
-        sd = sum(L.egso_mix64(((int(i) << 32) | (int(s) & 0xFFFFFFFF)) ^ 0xA5A5A5A5A5A5A5A5)
+        sd = sum(L.egso_mix64(2 * int(i) + 2) * (2 * (int(s) & 0xFFFFFFFF) + 1)
                  for i, s in zip(ids[fit.astype(bool)], sc)) & (2**64 - 1)
         t = torch.tensor([int(fit.sum()), fd - (1 << 64) if fd >= 1 << 63 else fd, sd - (1 << 64) if sd >= 1 << 63 else sd],
                          dtype=torch.int64)
