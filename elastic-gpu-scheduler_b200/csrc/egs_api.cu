@@ -922,11 +922,11 @@ extern "C" int egs_rounds_stats(egs_handle *h, int64_t out[8]) {
 }
 
 // debug: cycle counters of k_resolve sections (only filled when built with -DEGS_RESOLVE_PROF)
-extern "C" int egs_debug_resolve_prof(egs_handle *h, long long out[12]) {
+extern "C" int egs_debug_resolve_prof(egs_handle *h, long long out[16]) {
   if (!h || !out) return EGS_ERR_BAD_ARG;
   Guard g(h);
-  if (!h->rounds.d_prof) { memset(out, 0, sizeof(long long) * 12); return EGS_OK; }
-  CK(h, cudaMemcpy(out, h->rounds.d_prof, sizeof(long long) * 12, cudaMemcpyDeviceToHost));
+  if (!h->rounds.d_prof) { memset(out, 0, sizeof(long long) * 16); return EGS_OK; }
+  CK(h, cudaMemcpy(out, h->rounds.d_prof, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
   return EGS_OK;
 }
 

@@ -37,6 +37,7 @@ struct alignas(16) Cand {           // payload of one candidate node (16-byte ch
   unsigned long long key;           // cand_key(score, node); 0 = empty
   int32_t rc[EGS_G], rm[EGS_G];
   int32_t mt, pad;
+  unsigned long long fterm, sbase;    // fit_term(node), score_base(node): hashed once, here
   int32_t sc[RS];
   uint32_t al[RS];
   uint8_t st[RS];
@@ -66,26 +67,6 @@ struct SelectArgs {
   unsigned long long *cta_lists;    // [grid][RS][RK]
   AggPart *cta_agg;                 // [grid][RS]
 };
-
-// sorted-descending list of RK keys held by lanes 0..RK-1; insert k (warp-uniform value)
-__device__ __forceinline__ void list_insert(unsigned long long &L, unsigned long long k, int lane) {
-  const unsigned gt = __ballot_sync(0xffffffffu, lane < RK && L > k);
-  const int pos = __popc(gt);
-  const unsigned long long up = __shfl_up_sync(0xffffffffu, L, 1);
-  if (lane == pos) L = k; else if (lane > pos && lane < RK) L = up;
-}
-// merge up to 32 candidate keys (one per lane, 0 = none) into the list
-__device__ __forceinline__ void list_merge(unsigned long long &L, unsigned long long cand, int lane) {
-  for (;;) {
-    const unsigned long long kth = __shfl_sync(0xffffffffu, L, RK - 1);
-    const unsigned b = __ballot_sync(0xffffffffu, cand > kth);
-    if (!b) break;
-    const int src = __ffs(b) - 1;
-    const unsigned long long k = __shfl_sync(0xffffffffu, cand, src);
-    list_insert(L, k, lane);
-    if (lane == src) cand = 0;
-  }
-}
 
 // 32 keys, one per lane -> sorted descending across the lanes (bitonic network, 15 exchange steps)
 __device__ __forceinline__ unsigned long long warp_sort_desc(unsigned long long v, int lane) {
@@ -251,6 +232,8 @@ __global__ void __launch_bounds__(256) k_merge(MergeArgs a) {
     if (key == 0) { if (f == 0) cd->key = 0; continue; }
     const size_t node = key_node(key);
     if (f == 0) { cd->key = key; cd->mt = a.mem_total[node]; cd->pad = 0; }
+    if (f == 1) cd->fterm = fit_term((uint32_t)node);
+    if (f == 2) cd->sbase = score_base((uint32_t)node);
     if (f < EGS_G) cd->rc[f] = a.core[node * EGS_G + f]; else cd->rm[f - EGS_G] = a.mem[node * EGS_G + f - EGS_G];
     for (int s2 = f; s2 < RS; s2 += 16) {
       uint8_t st = OPT_UNFIT; int32_t sc = 0; uint32_t al = 0;
@@ -410,7 +393,6 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
 #ifdef EGS_RESOLVE_PROF
   long long tprev = clock64();
 #endif
-  const int DK = D * RK;
   int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
   if (win != 0) {
     int t = t_in;
@@ -421,23 +403,25 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
       const uint32_t w = key_node(win);
       cp_async_wait_all();
       __syncwarp();
+      PROF_T(12)
       {
-        int rowv, mtv, scv; uint32_t alv; uint8_t st;
+        int rowv, mtv, scv; uint32_t alv; uint8_t st; unsigned long long ft, sb;
         if (S.hpay_node[s] == (int)w) {                            // warp-uniform: payload already in shared memory
           const Cand &cd = S.hpay[s];
-          rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0; mtv = cd.mt; st = cd.st[lane]; scv = cd.sc[lane]; alv = cd.al[lane];
+          rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0; mtv = cd.mt; st = cd.st[lane]; scv = cd.sc[lane]; alv = cd.al[lane]; ft = cd.fterm; sb = cd.sbase;
         } else {
           const Cand &cd = a.bufs[d].cand[s][S.cur[s][d]];
-          rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0; mtv = cd.mt; st = cd.st[lane]; scv = cd.sc[lane]; alv = cd.al[lane];
+          rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0; mtv = cd.mt; st = cd.st[lane]; scv = cd.sc[lane]; alv = cd.al[lane]; ft = cd.fterm; sb = cd.sbase;
         }
         if (lane < EGS_G) S.rc[t][lane] = rowv; else if (lane < 2 * EGS_G) S.rm[t][lane - EGS_G] = rowv;   // rc[8], rm[8] contiguous
-        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = mtv; S.dirty[t] = 0; S.fterm[t] = fit_term(w); S.sbase[t] = score_base(w); hset_add(S, w); }
+        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = mtv; S.dirty[t] = 0; S.fterm[t] = ft; S.sbase[t] = sb; hset_add(S, w); }
         if (st == OPT_NEW && S.observed[lane]) st = OPT_CACHED;   // lane == shape index
         S.st[lane][t] = st; S.al[lane][t] = alv;
         S.tkey[lane][t] = (st == OPT_CACHED || st == OPT_NEW) ? cand_key(scv, w) : 0ull;
         if (st == OPT_ABSENT) S.pmask[lane][t >> 5] |= 1u << (t & 31);
       }
       __syncwarp();
+      PROF_T(13)
       // it leaves the untracked lists lazily: only lists whose HEAD is this node advance now (entries deeper
       // in a list are skipped when they surface); then the changed heads get their payloads prefetched
       for (int i = lane; i < ns * D; i += 32) {
@@ -445,13 +429,23 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
         if (hk != 0 && key_node(hk) == w) list_head_update(S, i / D, i % D);
       }
       __syncwarp();
-      {
-        bool need = false;
-        if (lane < ns) { int dd; const unsigned long long k = best_head(S, lane, D, dd); need = (k ? (int)key_node(k) : -1) != S.hpay_node[lane]; }
-        for (unsigned rem = __ballot_sync(0xffffffffu, need); rem; rem &= rem - 1) prefetch_head(S, a, __ffs(rem) - 1, D, lane);
-        cp_async_commit();
+      PROF_T(14)
+      if (lane < ns) {                                            // lane == shape: its own 23 x 16 B copies, in lockstep
+        int dd; const unsigned long long k = best_head(S, lane, D, dd);
+        const int want = k ? (int)key_node(k) : -1;
+        if (want != S.hpay_node[lane]) {
+          S.hpay_node[lane] = want;
+          if (k) {
+            const char *src = reinterpret_cast<const char *>(&a.bufs[dd].cand[lane][S.cur[lane][dd]]);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&S.hpay[lane]);
+#pragma unroll
+            for (int q = 0; q < (int)(sizeof(Cand) / 16); q++)
+              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * 16), "l"(src + q * 16));
+          }
+        }
       }
-      PROF_T(10) PROF_C(11, 1)
+      cp_async_commit();
+      PROF_T(15) PROF_C(11, 1)
     }
     o_node = S.node[t];
     const int single = S.rq_single[s];
@@ -556,7 +550,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
   // ---- sequential replay
   int p = a.p0;
 #ifdef EGS_RESOLVE_PROF
-  long long prof[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64();
+  long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64();
 #endif
   while (p < a.p_limit) {
     const int rel = p - a.p0;
@@ -863,7 +857,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
   if (lane < ns && S.observed[lane]) a.obs_pending[a.set.slot[lane]] = 1;
   if (lane == 0) { a.done[0] = done; a.done[1] = nT; a.done[2] = reason; }
 #ifdef EGS_RESOLVE_PROF
-  if (lane == 0) for (int i = 0; i < 12; i++) atomicAdd((unsigned long long *)a.prof + i, (unsigned long long)prof[i]);
+  if (lane == 0) for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)a.prof + i, (unsigned long long)prof[i]);
 #endif
 }
 

@@ -75,8 +75,8 @@ static int rounds_ensure(egs_handle *h, int P) {
     CK(h, cudaMalloc(&R.d_bufs, sizeof(ShardBuf) * RD));
     CK(h, cudaMemsetAsync(R.d_bufs, 0, sizeof(ShardBuf) * RD, h->stream));
     CK(h, cudaMalloc(&R.d_done, sizeof(int32_t) * 4));
-    CK(h, cudaMalloc(&R.d_prof, sizeof(long long) * 12));
-    CK(h, cudaMemsetAsync(R.d_prof, 0, sizeof(long long) * 12, h->stream));
+    CK(h, cudaMalloc(&R.d_prof, sizeof(long long) * 16));
+    CK(h, cudaMemsetAsync(R.d_prof, 0, sizeof(long long) * 16, h->stream));
     CK(h, cudaMallocHost(&R.h_done, sizeof(int32_t) * 4));
     CK(h, cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem)));
   }
@@ -129,6 +129,16 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (h->timing) for (auto &e : ev) CK(h, cudaEventCreate(&e));
 
+  // distinct shapes of the whole batch, in order of first appearance: when they fit one round set the set
+  // is the same for every round and no per-round scan of the pod list is needed
+  std::vector<int> batch_shapes;
+  {
+    std::vector<char> seen(h->shapes.size(), 0);
+    for (int p = 0; p < P && (int)batch_shapes.size() <= RS; p++)
+      if (!seen[slots[p]]) { seen[slots[p]] = 1; batch_shapes.push_back(slots[p]); }
+  }
+  const bool one_set = (int)batch_shapes.size() <= RS;
+
   int p0 = 0;
   while (p0 < P) {
     // the round's shape set: distinct shapes in pod order until RS are collected
@@ -136,6 +146,10 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
     RoundSet set; set.n = 0;
     int plim = p0;
     const int pcap = std::min(P, p0 + 16384);    // a round never gets further (tracked table, list depth)
+    if (one_set) {
+      for (int q : batch_shapes) set.slot[set.n++] = q;
+      plim = pcap;
+    }
     for (; plim < pcap; plim++) {
       const int slot = slots[plim];
       bool found = false;
