@@ -461,12 +461,14 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
       const int g = __ffs(masks) - 1;
       const int c = S.rc[t][g], m = S.rm[t][g], rc = S.rq_core[s], rm = S.rq_mem[s];
       ok = (c >= rc && m >= rm) ? 1 : 0;
+      __syncwarp();                                               // all lanes have read before lane 0 writes
       if (lane == 0) {
         S.st[s][t] = OPT_ABSENT; S.tkey[s][t] = 0; S.pmask[s][t >> 5] = npm;
         S.afit[s] = nfit; S.afd[s] = nfd; S.asd[s] = nsd; S.dirty[t] = 1;
         if (ok) { S.rc[t][g] = c - rc; S.rm[t][g] = m - rm; }
       }
     } else {
+      __syncwarp();
       if (lane == 0) {
         S.st[s][t] = OPT_ABSENT; S.tkey[s][t] = 0; S.pmask[s][t >> 5] = npm;
         S.afit[s] = nfit; S.afd[s] = nfd; S.asd[s] = nsd; S.dirty[t] = 1;
@@ -494,6 +496,7 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
     const int r = rel & 63;
     S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fitc; S.o_fd[r] = ofd; S.o_sd[r] = osd; S.o_alloc[r] = o_masks;
   }
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
@@ -555,7 +558,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
   while (p < a.p_limit) {
     const int rel = p - a.p0;
     if ((rel >> 5) != cur_blk) { cur_blk = rel >> 5; myshape = nxshape; nxshape = load_block(cur_blk + 1); }
-    while (rel - flushed >= 32) { flush_outputs(S, a.out, a.p0 + flushed, flushed, 32, lane); flushed += 32; }
+    while (rel - flushed >= 32) { __syncwarp(); flush_outputs(S, a.out, a.p0 + flushed, flushed, 32, lane); flushed += 32; }
     const int ri = rel & 31;
     // ======== fast path: up to 4 consecutive pods with distinct single-container shapes, decided by four
     // 8-lane groups at once.  Preconditions make the decisions independent of each other's commits except
@@ -659,6 +662,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
           if (dup && j < Ws) Ws = j;
         }
         PROF_T(2)
+        __syncwarp();                                              // decisions (reads) are complete in every lane
         // ---- commits side by side: group leaders write disjoint rows (shape) and slots (node)
         if (grp < Ws) {
           int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
@@ -672,6 +676,7 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
             const int ok = (cc >= rq_c && mm >= rq_m) ? 1 : 0;      // GPUs.Transact gpu.go:164-171
             o_node = S.node[t];
             const unsigned long long nfd = fd - S.fterm[t], nsd = sd - score_term_b(S.sbase[t], key_score(win));
+            __syncwarp(Ws >= 4 ? 0xffffffffu : ((1u << (8 * Ws)) - 1u));   // every lane has read the row before its leader updates it
             if (gl == 0) {
               if (u >= 0 && !same) {                                 // this pod's filter Traded slot u
                 if (bk >= 0) { S.st[sgs][u] = OPT_CACHED; S.al[sgs][u] = 1u << (bk & 7); S.tkey[sgs][u] = tradekey; }
