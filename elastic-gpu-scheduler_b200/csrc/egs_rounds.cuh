@@ -662,42 +662,38 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
           if (dup && j < Ws) Ws = j;
         }
         PROF_T(2)
-        __syncwarp();                                              // decisions (reads) are complete in every lane
-        // ---- commits side by side: group leaders write disjoint rows (shape) and slots (node)
-        if (grp < Ws) {
-          int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
+        // ---- commits side by side: group leaders write disjoint rows (shape) and slots (node).
+        // Phase 1, every lane (safe indices for idle groups): read what the bind needs.
+        const bool act = grp < Ws;
+        const bool bindp = act && win != 0;
+        const int tb = bindp ? tw : 0;
+        const bool same = bindp && u == tb;                          // the node just Traded wins again (the common case)
+        const uint32_t masks = !bindp ? 1u : same ? (1u << (bk & 7)) : (S.al[sgs][tb] & 0xFFu);
+        const int gsel = __ffs(masks | 0x100u) - 1 & 7;
+        const int cc = S.rc[tb][gsel], mm = S.rm[tb][gsel];
+        const int okb = (cc >= rq_c && mm >= rq_m) ? 1 : 0;          // GPUs.Transact gpu.go:164-171
+        const int nodeb = S.node[tb];
+        const unsigned long long nfd = fd - S.fterm[tb], nsd = sd - score_term_b(S.sbase[tb], key_score(win));
+        __syncwarp();                                                // all reads done before any leader writes
+        // Phase 2, group leaders.
+        if (act && gl == 0) {
           const unsigned ubit = 1u << (u & 31);
-          if (win != 0) {
-            const int t = tw;
-            const bool same = u == t;                                // the node just Traded wins again (the common case)
-            const uint32_t masks = same ? (1u << (bk & 7)) : (S.al[sgs][t] & 0xFFu);
-            const int g = __ffs(masks) - 1;
-            const int cc = S.rc[t][g], mm = S.rm[t][g];
-            const int ok = (cc >= rq_c && mm >= rq_m) ? 1 : 0;      // GPUs.Transact gpu.go:164-171
-            o_node = S.node[t];
-            const unsigned long long nfd = fd - S.fterm[t], nsd = sd - score_term_b(S.sbase[t], key_score(win));
-            __syncwarp(Ws >= 4 ? 0xffffffffu : ((1u << (8 * Ws)) - 1u));   // every lane has read the row before its leader updates it
-            if (gl == 0) {
-              if (u >= 0 && !same) {                                 // this pod's filter Traded slot u
-                if (bk >= 0) { S.st[sgs][u] = OPT_CACHED; S.al[sgs][u] = 1u << (bk & 7); S.tkey[sgs][u] = tradekey; }
-                else S.st[sgs][u] = OPT_UNFIT;
-                S.pmask[sgs][u >> 5] &= ~ubit;
-              }
-              S.st[sgs][t] = OPT_ABSENT; S.tkey[sgs][t] = 0; S.pmask[sgs][t >> 5] |= 1u << (t & 31);   // node.go:90-92
-              S.afit[sgs] = fit - 1; S.afd[sgs] = nfd; S.asd[sgs] = nsd; S.dirty[t] = 1;
-              if (ok) { S.rc[t][g] = cc - rq_c; S.rm[t][g] = mm - rq_m; }
-            }
-            o_status = ok ? EGS_OK : EGS_ERR_TRANSACT;
-            o_masks = ok ? masks : 0;
-          } else if (gl == 0 && u >= 0) {                            // nothing fits; the Trade result still stands
-            if (bk >= 0) { S.st[sgs][u] = OPT_CACHED; S.al[sgs][u] = 1u << (bk & 7); S.tkey[sgs][u] = tradekey; S.afit[sgs] = fit; S.afd[sgs] = fd; S.asd[sgs] = sd; }
+          int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
+          if (u >= 0 && !same) {                                     // this pod's filter Traded slot u
+            if (bk >= 0) { S.st[sgs][u] = OPT_CACHED; S.al[sgs][u] = 1u << (bk & 7); S.tkey[sgs][u] = tradekey; }
             else S.st[sgs][u] = OPT_UNFIT;
             S.pmask[sgs][u >> 5] &= ~ubit;
           }
-          if (gl == 0) {
-            const int r = (rel + grp) & 63;
-            S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fit; S.o_fd[r] = fd; S.o_sd[r] = sd; S.o_alloc[r] = o_masks;
+          if (bindp) {
+            S.st[sgs][tb] = OPT_ABSENT; S.tkey[sgs][tb] = 0; S.pmask[sgs][tb >> 5] |= 1u << (tb & 31);   // node.go:90-92
+            S.afit[sgs] = fit - 1; S.afd[sgs] = nfd; S.asd[sgs] = nsd; S.dirty[tb] = 1;
+            if (okb) { S.rc[tb][gsel] = cc - rq_c; S.rm[tb][gsel] = mm - rq_m; }
+            o_node = nodeb; o_status = okb ? EGS_OK : EGS_ERR_TRANSACT; o_masks = okb ? masks : 0;
+          } else if (u >= 0 && bk >= 0) {                            // nothing fits elsewhere, but the Trade result stands
+            S.afit[sgs] = fit; S.afd[sgs] = fd; S.asd[sgs] = sd;
           }
+          const int r = (rel + grp) & 63;
+          S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fit; S.o_fd[r] = fd; S.o_sd[r] = sd; S.o_alloc[r] = o_masks;
         }
         __syncwarp();
         // ---- the rest (a head-win, or pods sharing a node) in pod order
