@@ -46,6 +46,22 @@ def parse():
     return ap.parse_args()
 
 
+def ncu_traffic():
+    """DRAM bytes per k_evaluate launch from the committed ncu --set full summary (profiles/), or None."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "evaluate_*_ncu.json")), reverse=True):
+        try:
+            with open(path) as f:
+                l0 = json.load(f)["launches"][0]
+            def mb(key):
+                v, unit = l0[key].split()[:2]
+                return float(v) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
+            return int(mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum")), os.path.basename(path)
+        except Exception:
+            continue
+    return None, None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -275,9 +291,11 @@ def main():
         ms_hot = e.profile_evaluate(req, iters=50)
         ms_cold = e.profile_evaluate(req, iters=20, flush_l2=True)
         ach = big_n * b_eval / (ms_big * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic()
         roof = {"bound": "hbm", "kernel": "k_evaluate (full evaluate: Trade on every node, no cache shortcut)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                "traffic": None, "bytes_per_eval": b_eval, "evals_per_launch": big_n, "ms_per_launch": ms_big,
+                "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes": big_n * b_eval,
+                "bytes_per_eval": b_eval, "evals_per_launch": big_n, "ms_per_launch": ms_big,
                 "note": "inputs larger than L2 (4M nodes x 64 B rows); timed with CUDA events on the launching stream",
                 "at_workload_n": {"nodes": w.n_nodes, "l2_hot_GBps": w.n_nodes * b_eval / (ms_hot * 1e-3) / 1e9,
                                   "l2_flushed_GBps": w.n_nodes * b_eval / (ms_cold * 1e-3) / 1e9,

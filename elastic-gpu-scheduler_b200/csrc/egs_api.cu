@@ -332,7 +332,7 @@ extern "C" int egs_unit_from_requests(int64_t core, int64_t mem, egs_unit *out) 
 // ------------------------------------------------------------------------------- node cache
 static int reset_nodes(egs_handle *h, int node0, int n, int full) {
   int ns = (int)h->shapes.size();
-  if (ns == 0 || n == 0) return EGS_OK;
+  if (ns == 0 || n <= 0) return EGS_OK;
   k_node_reset<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_st, (size_t)h->n_pad, ns, node0, n, full);
   CK(h, cudaGetLastError());
   return EGS_OK;

@@ -196,7 +196,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   }
   if (h->timing) for (auto &e : ev) cudaEventDestroy(e);
   const int n = h->hi - h->lo;
-  k_rounds_finalize<<<(n + 255) / 256, 256, 0, h->stream>>>(tb, R.d_obs, h->lo, h->hi);
+  if (n > 0) k_rounds_finalize<<<(n + 255) / 256, 256, 0, h->stream>>>(tb, R.d_obs, h->lo, h->hi);   // a shard may be empty
   k_clear_u8<<<(R.obs_cap + 255) / 256, 256, 0, h->stream>>>(R.d_obs, R.obs_cap);
   CK(h, cudaGetLastError());
   return EGS_OK;
