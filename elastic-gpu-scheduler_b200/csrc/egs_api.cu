@@ -43,6 +43,7 @@ struct egs_handle {
   int slot_cap = 0;
   uint8_t *d_st = nullptr; int32_t *d_sc = nullptr; uint8_t *d_al = nullptr;
   std::vector<Shape> shapes;
+  std::vector<char> slot_cold;            // option table of the slot holds only OPT_ABSENT (nothing evaluated yet)
   std::unordered_map<std::string, int> shape_ids;
   struct ShapeCacheEnt { uint64_t h; int slot; };
   std::vector<ShapeCacheEnt> shape_cache = std::vector<ShapeCacheEnt>(1024, ShapeCacheEnt{0, -1});   // open addressing
@@ -178,6 +179,7 @@ static int intern_slow(egs_handle *h, int C, const egs_unit *u, int *slot) {
   TRY(grow_slots(h, s + 1));
   Shape sh; sh.C = C; memset(sh.u, 0, sizeof sh.u); memcpy(sh.u, u, sizeof(egs_unit) * C);
   h->shapes.push_back(sh);
+  h->slot_cold.push_back(1);
   h->shape_ids.emplace(key, s);
   *slot = s;
   return EGS_OK;
@@ -364,7 +366,7 @@ static int load_rows(egs_handle *h, int node0, int n, int gpu_count, int mem_tot
   CK(h, cudaMemcpyAsync(h->d_mem + (size_t)node0 * EGS_G, sm, cells * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   CK(h, cudaMemcpyAsync(h->d_mem_total + node0, st, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
   TRY(reset_nodes(h, node0, n, fresh ? 1 : 0));
-  h->rounds.index_valid = false;
+  if (fresh && node0 == 0 && n >= h->max_nodes) std::fill(h->slot_cold.begin(), h->slot_cold.end(), 1);
   return EGS_OK;
 }
 
@@ -443,7 +445,6 @@ extern "C" int egs_state_dump(egs_handle *h, int node0, int n, int32_t *free_cor
   if (!h) return EGS_ERR_BAD_ARG;
   Guard g(h);
   if (node0 < 0 || n < 0 || node0 + n > h->max_nodes) return EGS_ERR_BAD_ARG;
-  TRY(rounds_sync_rows(h));
   size_t cells = (size_t)n * EGS_G;
   TRY(ensure_stage(h, cells * 2 * sizeof(int32_t)));
   int32_t *sc = (int32_t *)h->h_stage, *sm = sc + cells;
@@ -462,7 +463,6 @@ extern "C" int egs_state_dump(egs_handle *h, int node0, int n, int32_t *free_cor
 extern "C" int egs_state_snapshot(egs_handle *h) {
   if (!h) return EGS_ERR_BAD_ARG;
   Guard g(h);
-  TRY(rounds_sync_rows(h));
   const size_t rows = (size_t)h->n_pad * EGS_G * sizeof(int32_t);
   if (!h->d_snap_core) {
     CK(h, cudaMalloc(&h->d_snap_core, rows));
@@ -488,9 +488,9 @@ extern "C" int egs_state_restore(egs_handle *h) {
   CK(h, cudaMemcpyAsync(h->d_mem_total, h->d_snap_total, (size_t)h->n_pad * sizeof(int32_t), cudaMemcpyDeviceToDevice, h->stream));
   if (!h->shapes.empty())
     CK(h, cudaMemsetAsync(h->d_st, OPT_ABSENT, (size_t)h->n_pad * h->shapes.size(), h->stream));
+  std::fill(h->slot_cold.begin(), h->slot_cold.end(), 1);
   h->h_gpu_count = h->snap_gpu_count; h->h_mem_total = h->snap_mem_total;
   h->pods_map.clear(); h->pod_maps.clear(); h->released.clear(); free_auto_batches(h);
-  h->rounds.index_valid = false;
   return EGS_OK;
 }
 
@@ -513,7 +513,7 @@ static int gather(egs_handle *h, bool score, int n, const int32_t *node_ids, int
   int slot;
   TRY(intern(h, C, units, &slot));
   if (n == 0) return EGS_OK;
-  TRY(rounds_sync_rows(h));
+  h->slot_cold[slot] = 0;
   TRY(ensure_gather(h, (size_t)n));
   TRY(ensure_stage(h, (size_t)n * sizeof(int32_t)));
   GatherArgs a;
@@ -536,7 +536,6 @@ static int gather(egs_handle *h, bool score, int n, const int32_t *node_ids, int
     CK(h, cudaMemcpyAsync(h->h_result, h->d_result + 8, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     memcpy(out_score, h->h_stage, (size_t)n * sizeof(int32_t));
-    h->rounds.index_valid = false;
     return h->h_result[0] ? EGS_ERR_PANIC : EGS_OK;
   }
   if (single) k_gather_filter<true><<<grid, 256, 0, h->stream>>>(a); else k_gather_filter<false><<<grid, 256, 0, h->stream>>>(a);
@@ -544,7 +543,6 @@ static int gather(egs_handle *h, bool score, int n, const int32_t *node_ids, int
   CK(h, cudaMemcpyAsync(h->h_stage, h->d_fit, (size_t)n, cudaMemcpyDeviceToHost, h->stream));
   CK(h, cudaStreamSynchronize(h->stream));
   memcpy(out_fit, h->h_stage, (size_t)n);
-  h->rounds.index_valid = false;
   return EGS_OK;
 }
 
@@ -568,7 +566,6 @@ static int bind_or_peek(egs_handle *h, int consume, int node_id, int C, const eg
   int slot;
   TRY(intern(h, C, units, &slot));
   TRY(flush_pending(h));
-  TRY(rounds_sync_rows(h));
   BindArgs a;
   a.core = h->d_core; a.mem = h->d_mem; a.mem_total = h->d_mem_total; a.node = node_id;
   a.req = make_req(C, units); a.t = table(h, slot);
@@ -581,7 +578,6 @@ static int bind_or_peek(egs_handle *h, int consume, int node_id, int C, const eg
   CK(h, cudaStreamSynchronize(h->stream));
   memcpy(res4, h->h_result, 4 * sizeof(int32_t));
   if (consume) {
-    h->rounds.index_valid = false;
     if (res4[0] && !known) h->pods_map.insert(NodeUid{node_id, uid});     // node.go:150, before Transact
     if (res4[1] == EGS_OK) h->pod_maps.insert(uid);                       // scheduler.go:224
   }
@@ -627,10 +623,8 @@ static int apply_lists(egs_handle *h, int cancel, int node_id, int C, const egs_
       a.idx[c][j] = (int8_t)v;
     }
   }
-  TRY(rounds_sync_rows(h));
   k_apply<<<1, 1, 0, h->stream>>>(a);
   CK(h, cudaGetLastError());
-  h->rounds.index_valid = false;
   return EGS_OK;
 }
 
@@ -722,9 +716,8 @@ static int ensure_out(egs_handle *h, int P) {
 // EGS_MODE_RESCAN: one k_pass launch per pod, stream ordered.
 static int batch_rescan(egs_handle *h, int P, const int32_t *c_off, const egs_unit *units,
                         const std::vector<int> &slots, PodOut out) {
-  TRY(rounds_sync_rows(h));
-  h->rounds.index_valid = false;
   const int grid = (h->max_nodes + PASS_THREADS - 1) / PASS_THREADS;
+  for (int p = 0; p < P; p++) h->slot_cold[slots[p]] = 0;
   for (int p = 0; p < P; p++) {
     const int C = c_off[p + 1] - c_off[p];
     const egs_unit *u = units + c_off[p];
@@ -849,7 +842,6 @@ extern "C" int egs_shard_set(egs_handle *h, int rank, int world) {
   Guard g(h);
   h->rank = rank; h->world = world;
   egs_shard_range(h->max_nodes, rank, world, &h->lo, &h->hi);
-  h->rounds.index_valid = false;
   return EGS_OK;
 }
 extern "C" int egs_comm_unique_id(uint8_t out_id[128]) { return rounds_comm_unique_id(out_id); }
@@ -865,7 +857,6 @@ extern "C" int egs_profile_evaluate(egs_handle *h, int n_containers, const egs_u
   if (!h || iters < 1 || !out_ms_per_launch) return EGS_ERR_BAD_ARG;
   Guard g(h);
   TRY(check_units(n_containers, units));
-  TRY(rounds_sync_rows(h));
   const size_t np = (size_t)h->n_pad;
   if (!h->d_ev_fit) {
     CK(h, cudaMalloc(&h->d_ev_fit, np));
@@ -875,8 +866,9 @@ extern "C" int egs_profile_evaluate(egs_handle *h, int n_containers, const egs_u
   const size_t flush_bytes = (size_t)256 << 20;
   if (flush_l2 && !h->d_flush) CK(h, cudaMalloc(&h->d_flush, flush_bytes));
   EvalArgs a;
-  a.core = h->d_core; a.mem = h->d_mem; a.mem_total = h->d_mem_total; a.n = h->max_nodes; a.policy = h->policy;
+  a.core = h->d_core; a.mem = h->d_mem; a.mem_total = h->d_mem_total; a.lo = 0; a.n = h->max_nodes; a.policy = h->policy;
   a.req = make_req(n_containers, units); a.fit = h->d_ev_fit; a.score = h->d_ev_score; a.gpu = h->d_ev_gpu; a.plane = np;
+  a.v_fit = 1; a.v_unfit = 0;
   const bool single = is_single(n_containers, units);
   int items = 2;                                  // nodes per thread (tuning knob for experiments)
   if (const char *ev = getenv("EGS_EVAL_ITEMS")) items = atoi(ev);

@@ -170,10 +170,11 @@ __global__ void __launch_bounds__(PASS_THREADS) k_pass(PassArgs a) {
 // --------------------------------------------------------------------------------------------
 struct EvalArgs {
   const int32_t *core, *mem, *mem_total;
-  int n, policy;
+  int lo, n, policy;                                            // nodes [lo, lo + n)
   Req req;
-  uint8_t *fit; int32_t *score; uint8_t *gpu; size_t plane;   // gpu: [C][plane]
-};
+  uint8_t *fit; int32_t *score; uint8_t *gpu; size_t plane;     // gpu: [C][plane]; all indexed by node id
+  uint8_t v_fit, v_unfit;                                       // byte written for fit / unfit (1/0, or OPT_NEW/OPT_UNFIT
+};                                                              // when the target is an option table)
 
 template <bool SINGLE, int ITEMS>
 __global__ void __launch_bounds__(256) k_evaluate(EvalArgs a) {
@@ -181,17 +182,18 @@ __global__ void __launch_bounds__(256) k_evaluate(EvalArgs a) {
   int c[ITEMS][EGS_G], m[ITEMS][EGS_G];
 #pragma unroll
   for (int it = 0; it < ITEMS; it++) {
-    const int i = base + it * 256;
-    if (i < a.n) load_row(a.core, a.mem, (size_t)i, c[it], m[it]);
+    const int j = base + it * 256;
+    if (j < a.n) load_row(a.core, a.mem, (size_t)(a.lo + j), c[it], m[it]);
   }
 #pragma unroll
   for (int it = 0; it < ITEMS; it++) {
-    const int i = base + it * 256;
-    if (i >= a.n) continue;
+    const int j = base + it * 256;
+    if (j >= a.n) continue;
+    const int i = a.lo + j;
     int score; uint32_t masks;
     const int mt = SINGLE ? 0 : a.mem_total[i];
     const bool ok = trade_any(c[it], m[it], mt, a.req, SINGLE, a.policy, score, masks);
-    a.fit[i] = ok ? 1 : 0;
+    a.fit[i] = ok ? a.v_fit : a.v_unfit;
     a.score[i] = ok ? score : 0;
     if (SINGLE) a.gpu[i] = ok ? (uint8_t)masks : 0;
     else for (int k = 0; k < a.req.C; k++) a.gpu[(size_t)k * a.plane + i] = ok ? (uint8_t)(masks >> (8 * k)) : 0;

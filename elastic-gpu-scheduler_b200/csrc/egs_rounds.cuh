@@ -880,7 +880,6 @@ __global__ void k_clear_u8(uint8_t *p, int n) {
 struct egs_handle;
 
 struct RoundsState {
-  bool index_valid = false;
   void *comm = nullptr;             // ncclComm_t
   int32_t *d_pod_slot = nullptr; int pod_cap = 0;
   uint8_t *d_obs = nullptr; int obs_cap = 0;
@@ -894,7 +893,6 @@ static int batch_rescan(egs_handle *h, int P, const int32_t *c_off, const egs_un
                         const std::vector<int> &slots, PodOut out);
 static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_unit *units,
                         const std::vector<int> &slots, PodOut out);
-static int rounds_sync_rows(egs_handle *h);
 static void rounds_free(RoundsState *r);
 static int rounds_comm_unique_id(uint8_t out_id[128]);
 static int rounds_comm_init(egs_handle *h, const uint8_t id[128]);

@@ -40,8 +40,6 @@ static NcclApi *nccl_api() {
     }                                                                                    \
   } while (0)
 
-static int rounds_sync_rows(egs_handle *) { return EGS_OK; }   // rows always live in d_core/d_mem
-
 static void rounds_free(RoundsState *r) {
   if (r->comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)r->comm);
   void *dev[] = {r->d_pod_slot, r->d_obs, r->d_cta_lists, r->d_cta_agg, r->d_bufs, r->d_done, r->d_prof};
@@ -138,6 +136,38 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
       if (!seen[slots[p]]) { seen[slots[p]] = 1; batch_shapes.push_back(slots[p]); }
   }
   const bool one_set = (int)batch_shapes.size() <= RS;
+
+  // Cold shapes (option table still all-absent, e.g. a fresh or restored scheduler): ONE full-evaluate launch
+  // per shape over this shard's nodes fills the table (OPT_NEW / OPT_UNFIT) -- the HBM-roofline kernel,
+  // N * (8G + 5 + C) bytes each; k_select then finds nothing left to Trade for them.
+  if (h->hi > h->lo) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    int cold = 0;
+    for (int slot : batch_shapes) {
+      if ((int)batch_shapes.size() > RS && cold >= RS) break;
+      if (!h->slot_cold[slot]) continue;
+      if (!e0) { CK(h, cudaEventCreate(&e0)); CK(h, cudaEventCreate(&e1)); CK(h, cudaEventRecord(e0, h->stream)); }
+      const Shape &sh = h->shapes[slot];
+      EvalArgs ea;
+      ea.core = h->d_core; ea.mem = h->d_mem; ea.mem_total = h->d_mem_total; ea.lo = h->lo; ea.n = h->hi - h->lo;
+      ea.policy = h->policy; ea.req = make_req(sh.C, sh.u);
+      ea.fit = tb.st + (size_t)slot * tb.n_pad; ea.score = tb.sc + (size_t)slot * tb.n_pad;
+      ea.gpu = tb.al + (size_t)slot * EGS_C * tb.n_pad; ea.plane = tb.n_pad; ea.v_fit = OPT_NEW; ea.v_unfit = OPT_UNFIT;
+      if (is_single(sh.C, sh.u)) k_evaluate<true, 2><<<(ea.n + 511) / 512, 256, 0, h->stream>>>(ea);
+      else k_evaluate<false, 1><<<(ea.n + 255) / 256, 256, 0, h->stream>>>(ea);
+      cold++;
+    }
+    if (e0) {
+      CK(h, cudaEventRecord(e1, h->stream));
+      CK(h, cudaEventSynchronize(e1));
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+      h->k_launches[EGS_K_EVALUATE] += cold; h->k_ms[EGS_K_EVALUATE] += ms;
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+      CK(h, cudaGetLastError());
+    }
+  }
+  for (int slot : batch_shapes) h->slot_cold[slot] = 0;
+  for (int p = 0; p < P; p++) h->slot_cold[slots[p]] = 0;
 
   int p0 = 0;
   while (p0 < P) {
