@@ -84,3 +84,64 @@ int egsh_released_pod(void *h, void *pod) { return ((HostCtx *)h)->sch->Released
 const char *egsh_status(void *h) { return ret((HostCtx *)h, ((HostCtx *)h)->sch->Status()); }
 
 }  // extern "C"
+
+// ---- extender JSON codec (no GPU needed) ----------------------------------------------------------
+#include "extender_json.h"
+
+struct JsonCtx { NodeInterner nodes; ExtenderArgs args; BindingArgs bind; std::string buf; };
+
+extern "C" {
+void *egsj_new() { return new JsonCtx(); }
+void egsj_free(void *c) { delete (JsonCtx *)c; }
+// returns "" or the error; afterwards egsj_* accessors read the parsed request
+const char *egsj_parse_args(void *c, const char *json, int64_t len) {
+  JsonCtx *j = (JsonCtx *)c;
+  j->buf = ParseExtenderArgs(std::string_view(json, (size_t)len), &j->nodes, &j->args);
+  return j->buf.c_str();
+}
+int egsj_has_nodenames(void *c) { return ((JsonCtx *)c)->args.has_nodenames; }
+int egsj_n_nodes(void *c) { return (int)((JsonCtx *)c)->args.node_ids.size(); }
+const int32_t *egsj_node_ids(void *c) { return ((JsonCtx *)c)->args.node_ids.data(); }
+int egsj_interned(void *c) { return ((JsonCtx *)c)->nodes.size(); }
+const char *egsj_node_name(void *c, int id) { return ((JsonCtx *)c)->nodes.Name(id).c_str(); }
+// "ns\tname\tuid\tnodeName\n" then per container "C\tname\thasCore\tcore\thasMem\tmem\n", annotations "A\tk\tv\n"
+const char *egsj_pod_dump(void *c) {
+  JsonCtx *j = (JsonCtx *)c;
+  const Pod &p = j->args.pod;
+  std::string s = p.ns + "\t" + p.name + "\t" + p.uid + "\t" + p.node_name + "\n";
+  for (const auto &ct : p.containers) {
+    auto ci = ct.requests.find(kResourceGPUCore), mi = ct.requests.find(kResourceGPUMemory);
+    s += "C\t" + ct.name + "\t" + (ci != ct.requests.end() ? "1\t" + std::to_string(ci->second) : std::string("0\t0")) + "\t" +
+         (mi != ct.requests.end() ? "1\t" + std::to_string(mi->second) : std::string("0\t0")) + "\n";
+  }
+  for (const auto &kv : p.annotations) s += "A\t" + kv.first + "\t" + kv.second + "\n";
+  j->buf = s;
+  return j->buf.c_str();
+}
+const char *egsj_parse_binding(void *c, const char *json, int64_t len) {
+  JsonCtx *j = (JsonCtx *)c;
+  std::string e = ParseBindingArgs(std::string_view(json, (size_t)len), &j->bind);
+  j->buf = e.empty() ? ("\t" + j->bind.pod_name + "\t" + j->bind.pod_namespace + "\t" + j->bind.pod_uid + "\t" + j->bind.node) : e;
+  return j->buf.c_str();
+}
+int egsj_quantity(const char *q, int64_t *out) { return ParseQuantityValue(q, out) ? 1 : 0; }
+// names / failed as "\n"-separated lists ("name\tmsg" for failed)
+const char *egsj_encode_filter(void *c, const char *names, const char *failed, const char *error) {
+  JsonCtx *j = (JsonCtx *)c;
+  std::vector<std::string> nn; std::map<std::string, std::string> ff;
+  auto split = [](const std::string &s, auto f) { size_t b = 0; while (b < s.size()) { size_t e = s.find('\n', b); if (e == std::string::npos) e = s.size(); if (e > b) f(s.substr(b, e - b)); b = e + 1; } };
+  split(names, [&](const std::string &l) { nn.push_back(l); });
+  split(failed, [&](const std::string &l) { size_t t = l.find('\t'); ff[l.substr(0, t)] = t == std::string::npos ? "" : l.substr(t + 1); });
+  j->buf = EncodeFilterResult(nn, ff, error);
+  return j->buf.c_str();
+}
+const char *egsj_encode_priorities(void *c, const char *names, const int64_t *scores, int n) {
+  JsonCtx *j = (JsonCtx *)c;
+  std::vector<std::pair<std::string, int64_t>> v;
+  std::string s(names); size_t b = 0;
+  for (int i = 0; i < n; i++) { size_t e = s.find('\n', b); if (e == std::string::npos) e = s.size(); v.emplace_back(s.substr(b, e - b), scores[i]); b = e + 1; }
+  j->buf = EncodeHostPriorityList(v);
+  return j->buf.c_str();
+}
+const char *egsj_encode_binding(void *c, const char *error) { JsonCtx *j = (JsonCtx *)c; j->buf = EncodeBindingResult(error); return j->buf.c_str(); }
+}
