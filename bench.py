@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--pods", type=int, default=0, help="PROFILING ONLY: schedule a pod prefix (line is marked invalid)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--roofline-only", action="store_true", help="PROFILING ONLY: just the 4M-node k_evaluate leg (for ncu)")
     return ap.parse_args()
 
 
@@ -53,6 +54,8 @@ def ncu_traffic():
         try:
             with open(path) as f:
                 l0 = json.load(f)["launches"][0]
+            if int(l0["launch__grid_size"].split()[0]) < 7000:      # not the 4M-node launch (7813 CTAs)
+                continue
             def mb(key):
                 v, unit = l0[key].split()[:2]
                 return float(v) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[unit]
@@ -201,6 +204,14 @@ def main():
         box = [cap.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)
         e.comm_init(box[0])
+    if args.roofline_only:
+        big_n = 4_000_000
+        reps = (big_n + w.n_nodes - 1) // w.n_nodes
+        eb = egs_b200.Egs(w.policy, big_n, 8, local)
+        eb.state_load_bulk(0, w.gpus, w.mem_total, np.tile(w.core, (reps, 1))[:big_n], np.tile(w.mem, (reps, 1))[:big_n])
+        ms = eb.profile_evaluate([tuple(int(x) for x in w.units[0])], iters=8)
+        print(json.dumps({"roofline_only": True, "ms_per_launch": ms, "GBps": big_n * 70 / (ms * 1e-3) / 1e9}))
+        return
     e.state_load_bulk(0, w.gpus, w.mem_total, w.core, w.mem)
     e.snapshot()
     P = w.n_pods

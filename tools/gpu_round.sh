@@ -12,8 +12,8 @@ tail -c 1500 gpurun_out/bench_ref_${TAG}.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_${TAG}.csv \
     python bench.py --steps 1 --warmup 1 --pods 30000 --no-cpu > gpurun_out/ncu_bench_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_bench_${TAG}.log | cut -c1-300
-# full capture of the evaluate kernel (HBM-resident 4M-node launches come first in the roofline leg)
+# full capture of the evaluate kernel on the HBM-resident 4M-node cluster
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_evaluate -s 3 -c 2 -o gpurun_out/prof_evaluate_${TAG} -f \
-    python bench.py --steps 1 --warmup 0 --pods 2000 --no-cpu > gpurun_out/ncu_eval_${TAG}.log 2>&1
+    python bench.py --roofline-only > gpurun_out/ncu_eval_${TAG}.log 2>&1
 tail -2 gpurun_out/ncu_eval_${TAG}.log | cut -c1-300
 ls -la gpurun_out | tail -12
