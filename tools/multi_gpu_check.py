@@ -21,6 +21,8 @@ def main():
     cap = egs_b200.capi
     fails = 0
     cases = [(1, None, None, None), (2, None, 20000, None), (4, None, 60000, None), (3, None, 1500, 1), (4, 300, 6000, 0), (3, 300, 3000, 0)]
+    if os.environ.get("EGS_MGC_FAST"):
+        cases = [(4, None, 40000, None), (1, None, None, None), (2, 3000, 6000, None)]
     for cfg, nn, npods, pol in cases:
         w = egs_b200.workloads.config(cfg, n_nodes=nn, n_pods=npods, policy=pol)
         ref = None
