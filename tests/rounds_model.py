@@ -33,12 +33,12 @@ class Entry:
 
 
 class RoundsModel:
-    def __init__(self, policy: int, K: int = 32, T: int = 256, RS: int = 32, shards: int = 1):
-        self.policy, self.K, self.T, self.RS, self.D = policy, K, T, RS, shards
+    def __init__(self, policy: int, K: int = 32, T: int = 256, RS: int = 32, shards: int = 1, window: int = 1):
+        self.policy, self.K, self.T, self.RS, self.D, self.W = policy, K, T, RS, shards, window
         self.nodes: List[List[po.GPU]] = []
         self.tables: Dict[tuple, List[Entry]] = {}          # shape -> per-node entries
         self.obs_pending: Dict[tuple, bool] = {}
-        self.stats = dict(rounds=0, dry=0, full=0, shape=0)
+        self.stats = dict(rounds=0, dry=0, full=0, shape=0, windows=0, window_pods=0, cuts=0)
 
     # ---- state
     def add_node(self, core_alloc: int, mem_alloc: int) -> int:
@@ -124,6 +124,77 @@ class RoundsModel:
             done = 0
             p = p0
             while p < plim:
+                # ---- 4-wide window (device fast path): mono round, every shape observed, distinct shapes,
+                # <= 1 pending option per shape, room in the tracked table.  Decisions are taken from the SAME
+                # state, then cut at the first hazard, then committed in order WITHOUT being recomputed.
+                if self.W > 1 and mono and all(observed.values()) and len(tracked) + self.W <= self.T:
+                    win_shapes = []
+                    for q in range(self.W):
+                        if p + q >= plim or pods[p + q] in win_shapes or pods[p + q] not in lists:
+                            break
+                        win_shapes.append(pods[p + q])
+                    decs = []
+                    for s in win_shapes:
+                        pend = [n_ for n_, ent in tracked.items() if ent[s][0] == ABSENT]
+                        heads, dry = [], False
+                        for d in range(self.D):
+                            keys, more = lists[s][d]
+                            c = cur[s][d]
+                            while c < len(keys) and keys[c][1] in tracked:
+                                c += 1
+                            if c < len(keys):
+                                heads.append(keys[c])
+                            elif more:
+                                dry = True
+                        if len(pend) > 1 or dry:
+                            break
+                        u = pend[0] if pend else None
+                        topt = self._trade(rows_copy[u], s) if u is not None else None
+                        cands = [(-ent[s][1], n_) for n_, ent in tracked.items() if ent[s][0] in (CACHED, NEW)] + heads
+                        if topt is not None:
+                            cands.append((-topt.score, u))
+                        fitc, ofd, osd = agg[s]
+                        if topt is not None:
+                            fitc, ofd, osd = fitc + 1, (ofd + fit_term(u)) & MASK64, (osd + score_term(u, topt.score)) & MASK64
+                        w = min(cands)[1] if cands else None
+                        decs.append(dict(s=s, u=u, topt=topt, w=w, head=(w is not None and w not in tracked), agg=(fitc, ofd, osd)))
+                    nW = len(decs)
+                    for j in range(1, nW):                        # hazards
+                        if any(decs[i]["head"] or (decs[j]["u"] is not None and decs[j]["u"] == decs[i]["w"] and not decs[i]["head"]) for i in range(j)):
+                            nW = j
+                            self.stats["cuts"] += 1
+                            break
+                    if nW >= 2:
+                        self.stats["windows"] += 1
+                        self.stats["window_pods"] += nW
+                        for dec in decs[:nW]:
+                            s, u, topt, w = dec["s"], dec["u"], dec["topt"], dec["w"]
+                            fitc, ofd, osd = dec["agg"]
+                            if u is not None:                     # the Trade result of this pod's filter
+                                e = tracked[u][s]
+                                if topt is None:
+                                    e[0] = UNFIT
+                                else:
+                                    e[0], e[1], e[2] = CACHED, topt.score, topt.allocated
+                            agg[s] = [fitc, ofd, osd]
+                            if w is None:
+                                out.append(dict(node=-1, status=po.EGS_ERR_NOFIT, alloc=None, fit_count=fitc, fit_digest=ofd, score_digest=osd))
+                            else:
+                                if w not in tracked:
+                                    rows_copy[w] = self.nodes[w]
+                                    tracked[w] = {s2: [CACHED if (self.tables[s2][w].st == NEW) else self.tables[s2][w].st,
+                                                       self.tables[s2][w].score, self.tables[s2][w].alloc] for s2 in shapes}
+                                e = tracked[w][s]
+                                opt = po.GPUOption(request=list(s), allocated=e[2], score=e[1])
+                                e[0] = ABSENT
+                                agg[s] = [fitc - 1, (ofd - fit_term(w)) & MASK64, (osd - score_term(w, e[1])) & MASK64]
+                                ok = po.transact(rows_copy[w], opt)
+                                dirty.add(w)
+                                out.append(dict(node=w, status=po.EGS_OK if ok else po.EGS_ERR_TRANSACT, alloc=opt.allocated if ok else None,
+                                                fit_count=fitc, fit_digest=ofd, score_digest=osd))
+                            p += 1
+                            done += 1
+                        continue
                 s = pods[p]
                 if s not in lists:
                     self.stats["shape"] += 1

@@ -91,3 +91,47 @@ def test_early_termination_paths_are_exercised():
         for k in tot:
             tot[k] += m.stats[k]
     assert tot["dry"] > 0 and tot["full"] > 0 and tot["shape"] > 0, tot
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_windowed_decisions_with_hazard_cut_are_exact(seed):
+    """The 4-wide window of k_resolve: decisions taken from one state + the hazard rule == sequential."""
+    rng = np.random.default_rng(1000 + seed)
+    policy = seed % 2
+    n_nodes = int(rng.integers(2, 12))                            # tiny clusters: shapes collide on nodes all the time
+    nodes = _cluster(rng, n_nodes)
+    shapes = [tuple([(int(rng.choice([0, 5, 10, 25, 50])), int(rng.integers(1, 12)), 0)]) for _ in range(int(rng.integers(2, 9)))]
+    o = po.Scheduler(policy)
+    m = RoundsModel(policy, K=int(rng.choice([2, 4, 32])), T=int(rng.choice([8, 64])), RS=32, shards=int(rng.choice([1, 2])), window=4)
+    for core, mem, rows in nodes:
+        a = o.add_node(core, mem); m.add_node(core, mem)
+        if rows:
+            o.set_rows(a, *rows); m.set_rows(a, *rows)
+    uid = 0
+    for batch in range(2):
+        pods = [shapes[int(i)] for i in rng.integers(0, len(shapes), 300)]
+        got = m.schedule_batch(pods)
+        for p, (s, g) in enumerate(zip(pods, got)):
+            r = o.schedule_one(list(s), uid); uid += 1
+            assert g == dict(node=r["node"], status=r["status"], alloc=r["alloc"], fit_count=r["fit_count"],
+                             fit_digest=r["fit_digest"], score_digest=r["score_digest"]), (seed, batch, p)
+        for n in range(n_nodes):
+            assert m.rows(n) == o.rows(n)
+    assert m.stats["windows"] > 0
+
+
+def test_windows_and_cuts_happen():
+    tot = dict(windows=0, window_pods=0, cuts=0)
+    for seed in range(30):
+        rng = np.random.default_rng(1000 + seed)
+        nodes = _cluster(rng, int(rng.integers(2, 12)))
+        shapes = [tuple([(int(rng.choice([0, 5, 10, 25, 50])), int(rng.integers(1, 12)), 0)]) for _ in range(int(rng.integers(2, 9)))]
+        m = RoundsModel(seed % 2, K=4, T=64, RS=32, shards=1, window=4)
+        for core, mem, rows in nodes:
+            a = m.add_node(core, mem)
+            if rows:
+                m.set_rows(a, *rows)
+        m.schedule_batch([shapes[int(i)] for i in rng.integers(0, len(shapes), 300)])
+        for k in tot:
+            tot[k] += m.stats[k]
+    assert tot["windows"] > 100 and tot["cuts"] > 20 and tot["window_pods"] > 2 * tot["windows"], tot
