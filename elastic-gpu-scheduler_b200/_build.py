@@ -66,7 +66,21 @@ def build_host(force: bool = False) -> str:
     return LIBHOST
 
 
+LIBDEVHOST = os.path.join(LIBDIR, "libegs_devhost.so")
+
+
+def build_devhost(force: bool = False) -> str:
+    """The kernels' integer arithmetic (csrc/egs_device.cuh) compiled for the host: CPU-side tests only."""
+    src = os.path.join(CSRC, "host_test", "device_on_host.cu")
+    deps = [src, os.path.join(CSRC, "egs_device.cuh"), os.path.join(ROOT, "include", "egs.h")]
+    if force or _stale(LIBDEVHOST, deps):
+        os.makedirs(LIBDIR, exist_ok=True)
+        subprocess.check_call([nvcc_path()] + NVCC_FLAGS + ["-o", LIBDEVHOST, src])
+    return LIBDEVHOST
+
+
 def build_all(force: bool = False) -> None:
     build_synth(force)
     build_libegs(force)
     build_host(force)
+    build_devhost(force)

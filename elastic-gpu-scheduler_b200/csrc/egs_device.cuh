@@ -9,6 +9,25 @@
 #include <stdint.h>
 #include "../../include/egs.h"
 
+// The arithmetic below is also compiled for the HOST (tests/test_device_arith_host.py runs it against
+// the oracle without a GPU); device intrinsics are spelled through these macros.
+#ifdef __CUDA_ARCH__
+#define EGS_HD __host__ __device__ __forceinline__
+#define EGS_MAX3(a, b, c) __vimax3_s32((a), (b), (c))
+#define EGS_POPC(x) __popc(x)
+#define EGS_FFS(x) __ffs(x)
+#define EGS_MIN(a, b) min((a), (b))
+#define EGS_MAX(a, b) max((a), (b))
+#else
+#include <algorithm>
+#define EGS_HD __host__ __device__ inline
+#define EGS_MAX3(a, b, c) std::max(std::max((a), (b)), (c))
+#define EGS_POPC(x) __builtin_popcount(x)
+#define EGS_FFS(x) __builtin_ffs((int)(x))
+#define EGS_MIN(a, b) std::min((a), (b))
+#define EGS_MAX(a, b) std::max((a), (b))
+#endif
+
 #define EGS_PAD INT32_MIN
 #define EGS_G EGS_MAX_GPUS
 #define EGS_C EGS_MAX_CONTAINERS
@@ -73,29 +92,29 @@ __device__ __forceinline__ void load_row(const int32_t *__restrict__ core, const
 //   * candidates are folded as key = q*8 + g: one max keeps the last maximal GPU.
 // Returns true when some GPU fits; score / gpu index by reference.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool trade_single(const int (&c)[EGS_G], const int (&m)[EGS_G], int rc, int rm,
-                                             int policy, int &score, int &gidx) {
+EGS_HD bool trade_single(const int (&c)[EGS_G], const int (&m)[EGS_G], int rc, int rm,
+                         int policy, int &score, int &gidx) {
   int bestkey = -1;
   if (policy == EGS_BINPACK) {
     unsigned ucmin = 0xFFFFFFFFu, ummin = 0xFFFFFFFFu;
     int cpre[EGS_G], csuf[EGS_G], mpre[EGS_G], msuf[EGS_G];
     cpre[0] = INT32_MIN; mpre[0] = INT32_MIN; csuf[EGS_G - 1] = INT32_MIN; msuf[EGS_G - 1] = INT32_MIN;
 #pragma unroll
-    for (int g = 0; g < EGS_G; g++) { ucmin = min(ucmin, (unsigned)c[g]); ummin = min(ummin, (unsigned)m[g]); }
+    for (int g = 0; g < EGS_G; g++) { ucmin = EGS_MIN(ucmin, (unsigned)c[g]); ummin = EGS_MIN(ummin, (unsigned)m[g]); }
 #pragma unroll
-    for (int g = 1; g < EGS_G; g++) { cpre[g] = max(cpre[g - 1], c[g - 1]); mpre[g] = max(mpre[g - 1], m[g - 1]); }
+    for (int g = 1; g < EGS_G; g++) { cpre[g] = EGS_MAX(cpre[g - 1], c[g - 1]); mpre[g] = EGS_MAX(mpre[g - 1], m[g - 1]); }
 #pragma unroll
-    for (int g = EGS_G - 2; g >= 0; g--) { csuf[g] = max(csuf[g + 1], c[g + 1]); msuf[g] = max(msuf[g + 1], m[g + 1]); }
+    for (int g = EGS_G - 2; g >= 0; g--) { csuf[g] = EGS_MAX(csuf[g + 1], c[g + 1]); msuf[g] = EGS_MAX(msuf[g + 1], m[g + 1]); }
     const int cmin = (int)ucmin, mmin = (int)ummin;
 #pragma unroll
     for (int g = 0; g < EGS_G; g++) {
       const bool ok = (c[g] >= rc) && (m[g] >= rm);         // CanAllocate gpu.go:55; PAD rows fail
       const int nc = c[g] - rc, nm = m[g] - rm;             // GPU.Add gpu.go:36-37
-      const int cmx = __vimax3_s32(cpre[g], csuf[g], nc), cmn = min(cmin, nc);
-      const int mmx = __vimax3_s32(mpre[g], msuf[g], nm), mmn = min(mmin, nm);
+      const int cmx = EGS_MAX3(cpre[g], csuf[g], nc), cmn = EGS_MIN(cmin, nc);
+      const int mmx = EGS_MAX3(mpre[g], msuf[g], nm), mmn = EGS_MIN(mmin, nm);
       const int x = (mmx + cmx) - (mmn + cmn);
       const int key = ok ? ((x >> 2) * 8 + g) : -1;
-      bestkey = max(bestkey, key);
+      bestkey = EGS_MAX(bestkey, key);
     }
     score = (bestkey >> 3) * 100;
   } else {                                                   // Spread.Rate == 0 (rater.go:56-59): last feasible GPU
@@ -121,7 +140,12 @@ struct TradeCtx {
   bool found;
 };
 
-__device__ __noinline__ void trade_leaf(TradeCtx &t) {  // gpu.go:73-93
+#ifdef __CUDA_ARCH__
+#define EGS_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define EGS_HD_NOINLINE __host__ __device__ inline
+#endif
+EGS_HD_NOINLINE void trade_leaf(TradeCtx &t) {  // gpu.go:73-93
   int s = 0;
   if (t.policy == EGS_BINPACK) {
     // rateIndexes: containers holding exactly one GPU (gpu.go:76-83); k = distinct GPUs (rater.go:19-30)
@@ -129,15 +153,15 @@ __device__ __noinline__ void trade_leaf(TradeCtx &t) {  // gpu.go:73-93
 #pragma unroll 1
     for (int i = 0; i < t.r->C; i++) {
       uint32_t mk = (t.masks >> (8 * i)) & 0xFFu;
-      if (__popc(mk) == 1) used |= mk;
+      if (EGS_POPC(mk) == 1) used |= mk;
     }
-    int k = __popc(used);
+    int k = EGS_POPC(used);
     int cmin = INT32_MAX, cmax = INT32_MIN, mmin = INT32_MAX, mmax = INT32_MIN;
 #pragma unroll 1
     for (int g = 0; g < EGS_G; g++) {
       if (t.c[g] == EGS_PAD) continue;
-      cmin = min(cmin, t.c[g]); cmax = max(cmax, t.c[g]);
-      mmin = min(mmin, t.m[g]); mmax = max(mmax, t.m[g]);
+      cmin = EGS_MIN(cmin, t.c[g]); cmax = EGS_MAX(cmax, t.c[g]);
+      mmin = EGS_MIN(mmin, t.m[g]); mmax = EGS_MAX(mmax, t.m[g]);
     }
     int range = (mmax + cmax - mmin - cmin) / 2;
     s = range / (k + 1) * 100;
@@ -149,7 +173,7 @@ __device__ __noinline__ void trade_leaf(TradeCtx &t) {  // gpu.go:73-93
 }
 
 template <int CI>
-__device__ __noinline__ void trade_dfs(TradeCtx &t) {
+EGS_HD_NOINLINE void trade_dfs(TradeCtx &t) {
   if (CI == t.r->C) { trade_leaf(t); return; }
   const int rc = t.r->core[CI], rm = t.r->mem[CI], cnt = t.r->cnt[CI];
   const uint32_t keep = t.masks & ~(0xFFu << (8 * CI));
@@ -179,10 +203,10 @@ __device__ __noinline__ void trade_dfs(TradeCtx &t) {
   t.masks = keep;
 }
 template <>
-__device__ __noinline__ void trade_dfs<EGS_C>(TradeCtx &t) { trade_leaf(t); }
+EGS_HD_NOINLINE void trade_dfs<EGS_C>(TradeCtx &t) { trade_leaf(t); }
 
-__device__ __forceinline__ bool trade_general(const int (&c)[EGS_G], const int (&m)[EGS_G], int mem_total,
-                                              const Req &r, int policy, int &score, uint32_t &masks) {
+EGS_HD bool trade_general(const int (&c)[EGS_G], const int (&m)[EGS_G], int mem_total,
+                          const Req &r, int policy, int &score, uint32_t &masks) {
   TradeCtx t;
 #pragma unroll
   for (int g = 0; g < EGS_G; g++) { t.c[g] = c[g]; t.m[g] = m[g]; }
@@ -198,8 +222,8 @@ __host__ __device__ __forceinline__ bool req_is_single(const Req &r) {
 }
 
 // Trade dispatch.  `masks` packs one u8 GPU mask per container.
-__device__ __forceinline__ bool trade_any(const int (&c)[EGS_G], const int (&m)[EGS_G], int mem_total,
-                                          const Req &r, bool single, int policy, int &score, uint32_t &masks) {
+EGS_HD bool trade_any(const int (&c)[EGS_G], const int (&m)[EGS_G], int mem_total,
+                      const Req &r, bool single, int policy, int &score, uint32_t &masks) {
   if (single) {
     int g;
     bool ok = trade_single(c, m, r.core[0], r.mem[0], policy, score, g);
@@ -211,8 +235,8 @@ __device__ __forceinline__ bool trade_any(const int (&c)[EGS_G], const int (&m)[
 
 // GPUs.Transact gpu.go:153-175 on the node's rows in global memory (one thread).
 // Returns true on success; on failure the Adds already made stay (no rollback).
-__device__ __forceinline__ bool transact_row(int32_t *core, int32_t *mem, int mem_total, const Req &r,
-                                             uint32_t masks) {
+EGS_HD bool transact_row(int32_t *core, int32_t *mem, int mem_total, const Req &r,
+                         uint32_t masks) {
   for (int i = 0; i < r.C; i++) {
     uint32_t mk = (masks >> (8 * i)) & 0xFFu;
     if (r.cnt[i] > 0) {
@@ -222,7 +246,7 @@ __device__ __forceinline__ bool transact_row(int32_t *core, int32_t *mem, int me
         core[g] = 0; mem[g] = 0;
       }
     } else if (mk) {
-      int g = __ffs(mk) - 1;
+      int g = EGS_FFS(mk) - 1;
       if (!(core[g] >= r.core[i] && mem[g] >= r.mem[i])) return false;
       core[g] -= r.core[i]; mem[g] -= r.mem[i];
     }
