@@ -23,7 +23,7 @@
  *   free_core[N][EGS_MAX_GPUS], free_mem[N][EGS_MAX_GPUS], mem_total[N]
  * (CoreTotal == 100 for every GPU, pkg/utils/types.go:6) plus, per interned
  * request shape s, the per-node option cache of node.go:19
- *   opt_state[s][N] (u8), opt_score[s][N] (i32), opt_alloc[s][N] (4 x u8 GPU masks).
+ *   opt_state[s][N] (u8), opt_score[s][N] (i32), opt_alloc[s][c][N] (u8 GPU mask of container c, c < 4).
  *
  * The INTEGRATION.md at the repo root shows the cgo binding.
  */
@@ -134,7 +134,11 @@ int egs_pod_released(egs_handle *h, uint64_t uid);   /* 1 / 0, scheduler.go:276-
 
 /* ---- batch decision loop (device resident) ---------------------------------- */
 
-/* Driver rule, identical to kube-scheduler's filter -> prioritize ->
+/* Limits of the device path: nodes with at most EGS_MAX_GPUS GPUs, pods with at most
+ * EGS_MAX_CONTAINERS containers, per-GPU memory units <= EGS_MAX_MEM_PER_GPU (use MiB, not bytes).
+ * Anything beyond is refused with EGS_ERR_BAD_ARG / EGS_ERR_OVERFLOW_GUARD -- never computed differently.
+ *
+ * Driver rule, identical to kube-scheduler's filter -> prioritize ->
  * bind round trip with ties broken to the first node: for each pod in order, filter
  * all nodes in index order, score the fit ones, winner = first fit node with the
  * maximum score, bind it.  Pod p has containers units[c_off[p] .. c_off[p+1]).
@@ -147,6 +151,13 @@ int egs_pod_released(egs_handle *h, uint64_t uid);   /* 1 / 0, scheduler.go:276-
  *   out_fit_digest[p]  sum over fit nodes of egs_mix64(2*node+1)                       (mod 2^64)
  *   out_score_digest[p] sum over fit nodes of egs_mix64(2*node+2) * (2*(u64)(u32)score + 1)             (mod 2^64)
  * The digests are sums so that node shards compose by addition.
+ *
+ * uids: NULL lets the library number the pods itself (pods awaiting scheduling are unknown to every
+ * podsMap); otherwise they must be pairwise distinct and not yet known (EGS_ERR_BAD_ARG).  A bind that
+ * reaches NodeAllocator.Add records the uid in that node's podsMap even when Transact fails (node.go:150);
+ * only a successful bind enters podMaps (scheduler.go:224) -- visible through egs_pod_known.
+ * EGS_MODE_AUTO == EGS_MODE_ROUNDS.  Both modes produce identical outputs; RESCAN is the literal
+ * one-pass-per-pod form (single shard only), ROUNDS the fast exact form.
  */
 enum egs_batch_mode {
   EGS_MODE_AUTO   = 0,
@@ -169,8 +180,11 @@ int egs_schedule_batch_device(egs_handle *h, int mode, int n_pods, const int32_t
 /* ---- node sharding over several GPUs (one handle per device) ----------------- */
 
 /* This handle owns nodes [lo, hi) of the max_nodes id space; rank/world describe the
- * shard order.  Every rank issues the same calls; the batch loop exchanges the
- * per-shape candidate lists with ncclAllGather once per round. */
+ * shard order (world <= 8).  Every rank issues the same node_set / state_load / batch calls with the
+ * FULL cluster; the batch loop exchanges the per-shape candidate buffers with ncclAllGather once per
+ * round and every rank returns identical per-pod outputs.  After a sharded batch a rank's rows and
+ * option tables are current only for its own range, so the single-pod verbs and egs_state_dump must be
+ * addressed to the owner of the node.  NCCL is resolved at run time with dlopen("libnccl.so.2"). */
 int egs_shard_set(egs_handle *h, int rank, int world);
 /* The contiguous node range [lo, hi) egs_shard_set gives rank `rank` of `world` (pure host
  * arithmetic, no handle): boundaries are multiples of 128, the last shard ends at max_nodes. */
