@@ -281,6 +281,26 @@ def main():
     e2e = {"value": P / (ms_e2e * 1e-3), "unit": "decisions/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e}
 
+    # ---- one extra, untimed step with the library's per-kernel CUDA-event timers on: who owns the step
+    breakdown = None
+    try:
+        st0 = e.rounds_stats()
+        e.profile_reset(True)
+        e.restore()
+        e.schedule_batch_device(w.c_off, w.units, dptrs, mode=mode)
+        st1 = e.rounds_stats()
+        ms = {"k_evaluate": e.profile_get(cap.EGS_K_EVALUATE)[1], "k_select": e.profile_get(cap.EGS_K_SELECT)[1],
+              "k_merge+allgather": e.profile_get(4)[1], "k_resolve": e.profile_get(cap.EGS_K_RESOLVE)[1]}
+        tot = sum(ms.values()) or 1.0
+        breakdown = {"ms": ms, "share": {k: v / tot for k, v in ms.items()},
+                     "rounds": st1["rounds"] - st0["rounds"], "tracked_nodes": st1["tracked"] - st0["tracked"],
+                     "stops": {k: st1[k] - st0[k] for k in ("stop_limit", "stop_shape", "stop_tracked_full", "stop_list_dry")},
+                     "note": "device time per kernel of one untimed step (events between launches, includes gaps); "
+                             "k_resolve is one warp bound by dependent-instruction latency, not by memory"}
+        e.profile_reset(False)
+    except Exception as ex:  # never let instrumentation break the bench line
+        breakdown = {"error": repr(ex)}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -340,6 +360,7 @@ def main():
             "l2": "256 MB buffer written between timed steps (L2 flush); within a step the 6.4 MB state is "
                   "L2-resident by construction"}),
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        "step_breakdown": breakdown,
     }
     if args.pods:
         line["profiling_subset"] = True
