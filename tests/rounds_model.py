@@ -160,7 +160,8 @@ class RoundsModel:
                         decs.append(dict(s=s, u=u, topt=topt, w=w, head=(w is not None and w not in tracked), agg=(fitc, ofd, osd)))
                     nW = len(decs)
                     for j in range(1, nW):                        # hazards
-                        if any(decs[i]["head"] or (decs[j]["u"] is not None and decs[j]["u"] == decs[i]["w"] and not decs[i]["head"]) for i in range(j)):
+                        if any((decs[i]["head"] and not getattr(self, "relax_head", False)) or
+                               (decs[j]["u"] is not None and decs[j]["u"] == decs[i]["w"] and not decs[i]["head"]) for i in range(j)):
                             nW = j
                             self.stats["cuts"] += 1
                             break

@@ -135,3 +135,26 @@ def test_windows_and_cuts_happen():
         for k in tot:
             tot[k] += m.stats[k]
     assert tot["windows"] > 100 and tot["cuts"] > 20 and tot["window_pods"] > 2 * tot["windows"], tot
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_relaxed_head_cut_and_wider_windows_stay_exact(seed):
+    """Round-2 candidate: no cut after a head-win (a second pick of the same node is a tracked win) and 8-wide windows."""
+    rng = np.random.default_rng(2000 + seed)
+    policy = seed % 2
+    nodes = _cluster(rng, int(rng.integers(2, 14)))
+    shapes = [tuple([(int(rng.choice([0, 5, 10, 25, 50])), int(rng.integers(1, 12)), 0)]) for _ in range(int(rng.integers(3, 12)))]
+    o = po.Scheduler(policy)
+    m = RoundsModel(policy, K=int(rng.choice([2, 4, 32])), T=64, RS=32, shards=int(rng.choice([1, 2])), window=8)
+    m.relax_head = True
+    for core, mem, rows in nodes:
+        a = o.add_node(core, mem); m.add_node(core, mem)
+        if rows:
+            o.set_rows(a, *rows); m.set_rows(a, *rows)
+    pods = [shapes[int(i)] for i in rng.integers(0, len(shapes), 400)]
+    got = m.schedule_batch(pods)
+    for uid, (s, g) in enumerate(zip(pods, got)):
+        r = o.schedule_one(list(s), uid)
+        assert g == dict(node=r["node"], status=r["status"], alloc=r["alloc"], fit_count=r["fit_count"],
+                         fit_digest=r["fit_digest"], score_digest=r["score_digest"]), (seed, uid)
+    assert m.stats["windows"] > 0
