@@ -765,20 +765,25 @@ static int batch_common(egs_handle *h, int mode, int P, const int32_t *c_off, co
     if (!dev.status) dev.status = h->d_o_status;
   }
   if (mode == EGS_MODE_AUTO) mode = EGS_MODE_ROUNDS;
+  int batch_rc = EGS_OK, n_done = P;
   if (mode == EGS_MODE_RESCAN) TRY(batch_rescan(h, P, c_off, units, slots, dev));
-  else if (mode == EGS_MODE_ROUNDS) TRY(batch_rounds(h, P, c_off, units, slots, dev));
+  else if (mode == EGS_MODE_ROUNDS) batch_rc = batch_rounds(h, P, c_off, units, slots, dev, &n_done);
   else return EGS_ERR_BAD_ARG;
 
-  // lazy uid bookkeeping: async copy of (node, status), applied on the next uid-dependent verb
-  PendingBatch pb; pb.n = P; pb.uid0 = h->next_uid;
-  if (uids) pb.uids.assign(uids, uids + P); else h->next_uid += (uint64_t)P;
-  CK(h, cudaMallocHost(&pb.h_node, sizeof(int32_t) * (size_t)P));
-  CK(h, cudaMallocHost(&pb.h_status, sizeof(int32_t) * (size_t)P));
-  CK(h, cudaMemcpyAsync(pb.h_node, dev.node, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaMemcpyAsync(pb.h_status, dev.status, sizeof(int32_t) * (size_t)P, cudaMemcpyDeviceToHost, h->stream));
-  CK(h, cudaEventCreateWithFlags(&pb.done, cudaEventDisableTiming));
-  CK(h, cudaEventRecord(pb.done, h->stream));
-  h->pending.push_back(std::move(pb));
+  // lazy uid bookkeeping: async copy of (node, status), applied on the next uid-dependent verb.  A batch that
+  // stopped on an error still records the pods it resolved: their binds are in the rows.
+  if (n_done > 0) {
+    PendingBatch pb; pb.n = n_done; pb.uid0 = h->next_uid;
+    if (uids) pb.uids.assign(uids, uids + n_done); else h->next_uid += (uint64_t)n_done;
+    CK(h, cudaMallocHost(&pb.h_node, sizeof(int32_t) * (size_t)n_done));
+    CK(h, cudaMallocHost(&pb.h_status, sizeof(int32_t) * (size_t)n_done));
+    CK(h, cudaMemcpyAsync(pb.h_node, dev.node, sizeof(int32_t) * (size_t)n_done, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaMemcpyAsync(pb.h_status, dev.status, sizeof(int32_t) * (size_t)n_done, cudaMemcpyDeviceToHost, h->stream));
+    CK(h, cudaEventCreateWithFlags(&pb.done, cudaEventDisableTiming));
+    CK(h, cudaEventRecord(pb.done, h->stream));
+    h->pending.push_back(std::move(pb));
+  }
+  if (batch_rc != EGS_OK) { cudaStreamSynchronize(h->stream); return batch_rc; }
 
   if (!device_out) {
     size_t sp = (size_t)P;
@@ -917,8 +922,7 @@ extern "C" int egs_rounds_stats(egs_handle *h, int64_t out[8]) {
 extern "C" int egs_debug_resolve_prof(egs_handle *h, long long out[16]) {
   if (!h || !out) return EGS_ERR_BAD_ARG;
   Guard g(h);
-  if (!h->rounds.d_prof) { memset(out, 0, sizeof(long long) * 16); return EGS_OK; }
-  CK(h, cudaMemcpy(out, h->rounds.d_prof, sizeof(long long) * 16, cudaMemcpyDeviceToHost));
+  memcpy(out, h->rounds.prof, sizeof(long long) * 16);
   return EGS_OK;
 }
 

@@ -6,14 +6,22 @@
 //
 //   k_select  (grid, N-proportional, shardable over GPUs): per node and per shape of the
 //             round: Trade every absent option (the full-evaluate work), fold fit count and
-//             digests, keep the top-RK candidates (score desc, node asc) per shape.
-//   k_merge   (one CTA per shape): fold the per-CTA lists, gather each candidate's payload
-//             (rows + its options for all round shapes) into the shard's candidate buffer.
+//             digests, keep the top-32 candidates (score desc, node asc) per CTA and shape.
+//   k_merge   (one CTA per shape): fold the per-CTA lists into ONE exact list of up to 128
+//             candidates (exact down to the largest 32nd key of a full CTA list), gather each
+//             candidate's payload (rows + its options for all round shapes) into the shard's
+//             candidate buffer.
 //   [ncclAllGather of the candidate buffers when the node list is sharded]
-//   k_resolve (ONE warp, shared-memory resident): replays the pods one after the other:
-//             winner = max(tracked nodes' options, best untracked list head), Transact,
-//             invalidate, outputs; stops early when a list runs dry or the tracked table is
-//             full; writes the tracked nodes back.
+//   k_resolve_mw (ONE CTA, one OWNER WARP per request shape, shared-memory resident): replays the
+//             pods in order.  The pods of one shape form a chain that only touches other shapes
+//             through the rows of the nodes it binds, so every owner warp prepares its next pod
+//             (best tracked option of its shape) on its own and the warps then pass a TICKET in
+//             pod order: inside the ticket the pod's pending option is Traded on the current
+//             rows, the winner = max(tracked options, best untracked list head) is bound
+//             (Transact on the shared-memory copy of the node) and the ticket moves on; outputs,
+//             digests and the owner's private tables are updated after the ticket was released.
+//             Stops early when a list runs dry or the tracked table is full; writes the tracked
+//             nodes back.
 //
 // Option states: OPT_NEW marks an option select evaluated AHEAD of the shape's next filter.
 // It is only valid while the node's rows stay unchanged; once a pod of that shape has run
@@ -24,29 +32,57 @@
 
 #define OPT_NEW 3
 
-#define RK 32        // candidates kept per (shard, shape) per round (one per lane)
-#define RT 256       // tracked (touched) nodes per round
-#define RS 32        // shapes per round
+#define RK 32        // candidates kept per (CTA, shape) in k_select (one per lane)
+#define RQMAX 4      // merged list: up to RQMAX*32 candidates per (shard, shape)
 #define RD 8         // shards
+#define RSMAX 96     // shapes per round set
 #define SEL_THREADS 128
 #define SEL_WARPS (SEL_THREADS / 32)
+#define MW_MAX_WARPS 16
 
-struct RoundSet { int n; int slot[RS]; };
+struct RoundDesc {                  // device resident: the round's shape set
+  int ns; int pad[3];
+  int slot[RSMAX];
+  Req reqs[RSMAX];
+};
 
-struct alignas(16) Cand {           // payload of one candidate node (16-byte chunks: cp.async)
-  unsigned long long key;           // cand_key(score, node); 0 = empty
-  int32_t rc[EGS_G], rm[EGS_G];
-  int32_t mt, pad;
-  unsigned long long fterm, sbase;    // fit_term(node), score_base(node): hashed once, here
-  int32_t sc[RS];
-  uint32_t al[RS];
-  uint8_t st[RS];
+struct RoundCtl {                   // device resident: progress of the batch, written by the resolver
+  int next_p, p_end, error, rounds;
+  long long pods, tracked;
+  long long stops[4];               // pod limit, shape outside the set, tracked table full, list dry
+  long long prof[16];
 };
-struct alignas(16) ShardBuf {       // what one shard contributes to a round
-  int32_t len[RS], more[RS], fit[RS], pad0;
-  unsigned long long fd[RS], sd[RS];
-  alignas(16) Cand cand[RS][RK];
+
+// One shard's candidate buffer (dynamic layout: shape capacity nsc, list depth rkm):
+//   int len[nsc], more[nsc], fit[nsc]; u64 fd[nsc], sd[nsc]; cand[nsc][rkm] of cand_bytes each
+// cand: key u64 @0 | rc[8] i32 @8 | rm[8] i32 @40 | mt i32 @72 | fterm u64 @80 | sbase u64 @88 |
+//       sc[nsc] i32 @96 | al[nsc] u32 @96+4nsc | st[nsc] u8 @96+8nsc
+struct BufLayout {
+  int nsc, rkm, cand_bytes, pad;
+  unsigned off_len, off_more, off_fit, off_fd, off_sd, off_cand;
+  unsigned long long bytes;         // per shard, multiple of 16
 };
+static inline BufLayout make_layout(int ns, int rkm) {
+  BufLayout L;
+  L.nsc = (ns + 15) / 16 * 16; L.rkm = rkm; L.cand_bytes = 96 + 9 * L.nsc; L.pad = 0;
+  unsigned o = 0;
+  L.off_len = o; o += 4u * L.nsc;
+  L.off_more = o; o += 4u * L.nsc;
+  L.off_fit = o; o += 4u * L.nsc;
+  o = (o + 15u) & ~15u;
+  L.off_fd = o; o += 8u * L.nsc;
+  L.off_sd = o; o += 8u * L.nsc;
+  L.off_cand = o;
+  L.bytes = (unsigned long long)o + (unsigned long long)L.nsc * rkm * L.cand_bytes;
+  return L;
+}
+#define CD_KEY 0
+#define CD_RC 8
+#define CD_RM 40
+#define CD_MT 72
+#define CD_FT 80
+#define CD_SB 88
+#define CD_SC 96
 
 struct AggPart { unsigned long long fd, sd; int fit, pad; };
 
@@ -57,15 +93,17 @@ __device__ __forceinline__ uint8_t *tb_st(const TableSet &t, int slot) { return 
 __device__ __forceinline__ int32_t *tb_sc(const TableSet &t, int slot) { return t.sc + (size_t)slot * t.n_pad; }
 __device__ __forceinline__ uint8_t *tb_al(const TableSet &t, int slot) { return t.al + (size_t)slot * EGS_C * t.n_pad; }
 
+__device__ __forceinline__ bool ctl_idle(const RoundCtl *c) { return c && (c->next_p >= c->p_end || c->error != 0); }
+
 struct SelectArgs {
   const int32_t *core, *mem, *mem_total;
-  int lo, hi, policy;               // this shard's node range
-  RoundSet set;
-  Req reqs[RS];
+  int lo, hi, policy, nsc;          // this shard's node range
+  const RoundDesc *rd;
   TableSet tb;
   const uint8_t *obs_pending;       // per slot: shape observed since its OPT_NEW options were made
-  unsigned long long *cta_lists;    // [grid][RS][RK]
-  AggPart *cta_agg;                 // [grid][RS]
+  unsigned long long *cta_lists;    // [grid][nsc][RK]
+  AggPart *cta_agg;                 // [grid][nsc]
+  const RoundCtl *ctl;              // batch finished -> nothing to do
 };
 
 // 32 keys, one per lane -> sorted descending across the lanes (bitonic network, 15 exchange steps)
@@ -93,94 +131,133 @@ __device__ __forceinline__ unsigned long long merge_top32(unsigned long long a, 
   }
   return v;
 }
+// 128-key lists: element e = q*32 + lane lives in register q of lane `lane`, descending in e.
+// A bitonic 128-sequence -> sorted descending (strides 64, 32 between registers; 16..1 by shuffle)
+__device__ __forceinline__ void bitonic128_desc(unsigned long long (&A)[RQMAX], int lane) {
+#pragma unroll
+  for (int q = 0; q < 2; q++) { const unsigned long long x = A[q], y = A[q + 2]; A[q] = x > y ? x : y; A[q + 2] = x > y ? y : x; }
+#pragma unroll
+  for (int q = 0; q < 4; q += 2) { const unsigned long long x = A[q], y = A[q + 1]; A[q] = x > y ? x : y; A[q + 1] = x > y ? y : x; }
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+#pragma unroll
+    for (int q = 0; q < RQMAX; q++) {
+      const unsigned long long o = __shfl_xor_sync(0xffffffffu, A[q], j);
+      A[q] = ((lane & j) == 0) ? (o > A[q] ? o : A[q]) : (o < A[q] ? o : A[q]);
+    }
+  }
+}
+// top 128 of (sorted 128-list A) U (sorted 32-list b)
+__device__ __forceinline__ void merge32_into128(unsigned long long (&A)[RQMAX], unsigned long long b, int lane) {
+  const unsigned long long kth = __shfl_sync(0xffffffffu, A[RQMAX - 1], 31);
+  const unsigned long long bmax = __shfl_sync(0xffffffffu, b, 0);
+  if (bmax <= kth) return;
+  const unsigned long long br = __shfl_sync(0xffffffffu, b, 31 - lane);
+  A[RQMAX - 1] = A[RQMAX - 1] > br ? A[RQMAX - 1] : br;
+  bitonic128_desc(A, lane);
+}
+// top 128 of two sorted 128-lists
+__device__ __forceinline__ void merge128(unsigned long long (&A)[RQMAX], const unsigned long long (&B)[RQMAX], int lane) {
+#pragma unroll
+  for (int q = 0; q < RQMAX; q++) {
+    const unsigned long long br = __shfl_sync(0xffffffffu, B[RQMAX - 1 - q], 31 - lane);
+    A[q] = A[q] > br ? A[q] : br;
+  }
+  bitonic128_desc(A, lane);
+}
 
 // --------------------------------------------------------------------------------------------
 // k_select
 // --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
-  __shared__ unsigned long long s_list[SEL_WARPS][RS][RK];
-  __shared__ AggPart s_agg[SEL_WARPS][RS];
-  __shared__ Req s_reqs[RS];          // kernel params are indexed dynamically: stage them in smem
-  __shared__ int s_slot[RS];
+  __shared__ unsigned long long s_list[SEL_WARPS][32][RK];
+  __shared__ AggPart s_agg[SEL_WARPS][32];
+  __shared__ Req s_reqs[32];          // the round descriptor is indexed dynamically: stage it in smem
+  __shared__ int s_slot[32];
+  if (ctl_idle(a.ctl)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * SEL_WARPS + warp, nwarps = gridDim.x * SEL_WARPS;
-  if (threadIdx.x < RS) { s_slot[threadIdx.x] = a.set.slot[threadIdx.x]; s_reqs[threadIdx.x] = a.reqs[threadIdx.x]; }
-  __syncthreads();
-  for (int s = lane; s < RS; s += 32) { s_agg[warp][s].fd = 0; s_agg[warp][s].sd = 0; s_agg[warp][s].fit = 0; }
-  for (int i = lane; i < RS * RK; i += 32) (&s_list[warp][0][0])[i] = 0;
-  __syncwarp();
+  const int ns = a.rd->ns;
   static_assert(RK == 32, "top-K lists are one key per lane");
   const int n_chunks = (a.hi - a.lo + 127) / 128;
-  for (int chunk = gwarp; chunk < n_chunks; chunk += nwarps) {
-    const int base = a.lo + chunk * 128 + lane;               // lane handles nodes base + 32*j: tied scores arrive in key order
-    unsigned long long h1[4], h2[4];                          // per-node digest hashes, shared by all shapes
+  for (int g0 = 0; g0 < ns; g0 += 32) {                          // shape groups of 32
+    const int gn = min(32, ns - g0);
+    __syncthreads();
+    if (threadIdx.x < gn) { s_slot[threadIdx.x] = a.rd->slot[g0 + threadIdx.x]; s_reqs[threadIdx.x] = a.rd->reqs[g0 + threadIdx.x]; }
+    for (int s = lane; s < 32; s += 32) { s_agg[warp][s].fd = 0; s_agg[warp][s].sd = 0; s_agg[warp][s].fit = 0; }
+    for (int i = lane; i < 32 * RK; i += 32) (&s_list[warp][0][0])[i] = 0;
+    __syncthreads();
+    for (int chunk = gwarp; chunk < n_chunks; chunk += nwarps) {
+      const int base = a.lo + chunk * 128 + lane;               // lane handles nodes base + 32*j: tied scores arrive in key order
+      unsigned long long h1[4], h2[4];                          // per-node digest hashes, shared by all shapes
 #pragma unroll
-    for (int j = 0; j < 4; j++) { h1[j] = fit_term((uint32_t)(base + 32 * j)); h2[j] = score_base((uint32_t)(base + 32 * j)); }
-    for (int s = 0; s < a.set.n; s++) {
-      const int slot = s_slot[s];
-      uint8_t *stp = tb_st(a.tb, slot);
-      int32_t *scp = tb_sc(a.tb, slot);
-      uint8_t *alp = tb_al(a.tb, slot);
-      const bool pending = a.obs_pending[slot] != 0;
-      const Req &r = s_reqs[s];
-      const bool single = req_is_single(r);
-      uint8_t st[4]; int sc[4];
+      for (int j = 0; j < 4; j++) { h1[j] = fit_term((uint32_t)(base + 32 * j)); h2[j] = score_base((uint32_t)(base + 32 * j)); }
+      for (int s = 0; s < gn; s++) {
+        const int slot = s_slot[s];
+        uint8_t *stp = tb_st(a.tb, slot);
+        int32_t *scp = tb_sc(a.tb, slot);
+        uint8_t *alp = tb_al(a.tb, slot);
+        const bool pending = a.obs_pending[slot] != 0;
+        const Req &r = s_reqs[s];
+        const bool single = req_is_single(r);
+        uint8_t st[4]; int sc[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int i = base + 32 * j;
-        st[j] = i < a.hi ? stp[i] : (uint8_t)OPT_UNFIT;
-        sc[j] = i < a.hi ? scp[i] : 0;
-      }
-      unsigned long long key[4], fd = 0, sd = 0;
-      int fit = 0;
+        for (int j = 0; j < 4; j++) {
+          const int i = base + 32 * j;
+          st[j] = i < a.hi ? stp[i] : (uint8_t)OPT_UNFIT;
+          sc[j] = i < a.hi ? scp[i] : 0;
+        }
+        unsigned long long key[4], fd = 0, sd = 0;
+        int fit = 0;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const int i = base + 32 * j;
-        key[j] = 0;
-        if (i >= a.hi) continue;
-        const uint8_t st0 = st[j];
-        if (st[j] == OPT_NEW && pending) st[j] = OPT_CACHED;
-        if (st[j] == OPT_ABSENT) {                             // full evaluate (gpu.go:65-129)
-          int c[EGS_G], m[EGS_G]; uint32_t masks;
-          load_row(a.core, a.mem, (size_t)i, c, m);
-          if (trade_any(c, m, a.mem_total[i], r, single, a.policy, sc[j], masks)) {
-            st[j] = OPT_NEW;
-            scp[i] = sc[j];
-            for (int k = 0; k < r.C; k++) alp[(size_t)k * a.tb.n_pad + i] = (uint8_t)(masks >> (8 * k));
-          } else {
-            st[j] = OPT_UNFIT;
+        for (int j = 0; j < 4; j++) {
+          const int i = base + 32 * j;
+          key[j] = 0;
+          if (i >= a.hi) continue;
+          const uint8_t st0 = st[j];
+          if (st[j] == OPT_NEW && pending) st[j] = OPT_CACHED;
+          if (st[j] == OPT_ABSENT) {                             // full evaluate (gpu.go:65-129)
+            int c[EGS_G], m[EGS_G]; uint32_t masks;
+            load_row(a.core, a.mem, (size_t)i, c, m);
+            if (trade_any(c, m, a.mem_total[i], r, single, a.policy, sc[j], masks)) {
+              st[j] = OPT_NEW;
+              scp[i] = sc[j];
+              for (int k = 0; k < r.C; k++) alp[(size_t)k * a.tb.n_pad + i] = (uint8_t)(masks >> (8 * k));
+            } else {
+              st[j] = OPT_UNFIT;
+            }
+          }
+          if (st[j] != st0) stp[i] = st[j];
+          if (st[j] == OPT_CACHED || st[j] == OPT_NEW) {
+            key[j] = cand_key(sc[j], (uint32_t)i);
+            fit++; fd += h1[j]; sd += score_term_b(h2[j], sc[j]);
           }
         }
-        if (st[j] != st0) stp[i] = st[j];
-        if (st[j] == OPT_CACHED || st[j] == OPT_NEW) {
-          key[j] = cand_key(sc[j], (uint32_t)i);
-          fit++; fd += h1[j]; sd += score_term_b(h2[j], sc[j]);
-        }
-      }
-      fit = warp_sum_i32(fit); fd = warp_sum_u64(fd); sd = warp_sum_u64(sd);
-      if (lane == 0) { s_agg[warp][s].fit += fit; s_agg[warp][s].fd += fd; s_agg[warp][s].sd += sd; }
-      // top-32 of this warp for shape s: sort 32 keys, merge sorted lists
-      unsigned long long L = s_list[warp][s][lane];
-      bool changed = false;
+        fit = warp_sum_i32(fit); fd = warp_sum_u64(fd); sd = warp_sum_u64(sd);
+        if (lane == 0) { s_agg[warp][s].fit += fit; s_agg[warp][s].fd += fd; s_agg[warp][s].sd += sd; }
+        // top-32 of this warp for shape s: sort 32 keys, merge sorted lists
+        unsigned long long L = s_list[warp][s][lane];
+        bool changed = false;
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const unsigned long long kth = __shfl_sync(0xffffffffu, L, RK - 1);
-        if (__ballot_sync(0xffffffffu, key[j] > kth)) { L = merge_top32(L, warp_sort_desc(key[j], lane), lane); changed = true; }
+        for (int j = 0; j < 4; j++) {
+          const unsigned long long kth = __shfl_sync(0xffffffffu, L, RK - 1);
+          if (__ballot_sync(0xffffffffu, key[j] > kth)) { L = merge_top32(L, warp_sort_desc(key[j], lane), lane); changed = true; }
+        }
+        if (changed) s_list[warp][s][lane] = L;
+        __syncwarp();
       }
-      if (changed) s_list[warp][s][lane] = L;
-      __syncwarp();
     }
-  }
-  __syncthreads();
-  // fold the warps of this CTA: warp w owns shapes s == w (mod SEL_WARPS)
-  for (int s = warp; s < a.set.n; s += SEL_WARPS) {
-    unsigned long long L = s_list[0][s][lane];
-    for (int w = 1; w < SEL_WARPS; w++) L = merge_top32(L, s_list[w][s][lane], lane);
-    if (lane < RK) a.cta_lists[((size_t)blockIdx.x * RS + s) * RK + lane] = L;
-    if (lane == 0) {
-      AggPart t; t.fd = 0; t.sd = 0; t.fit = 0; t.pad = 0;
-      for (int w = 0; w < SEL_WARPS; w++) { t.fd += s_agg[w][s].fd; t.sd += s_agg[w][s].sd; t.fit += s_agg[w][s].fit; }
-      a.cta_agg[(size_t)blockIdx.x * RS + s] = t;
+    __syncthreads();
+    // fold the warps of this CTA: warp w owns shapes s == w (mod SEL_WARPS)
+    for (int s = warp; s < gn; s += SEL_WARPS) {
+      unsigned long long L = s_list[0][s][lane];
+      for (int w = 1; w < SEL_WARPS; w++) L = merge_top32(L, s_list[w][s][lane], lane);
+      a.cta_lists[((size_t)blockIdx.x * a.nsc + g0 + s) * RK + lane] = L;
+      if (lane == 0) {
+        AggPart t; t.fd = 0; t.sd = 0; t.fit = 0; t.pad = 0;
+        for (int w = 0; w < SEL_WARPS; w++) { t.fd += s_agg[w][s].fd; t.sd += s_agg[w][s].sd; t.fit += s_agg[w][s].fit; }
+        a.cta_agg[(size_t)blockIdx.x * a.nsc + g0 + s] = t;
+      }
     }
   }
 }
@@ -190,270 +267,368 @@ __global__ void __launch_bounds__(SEL_THREADS) k_select(SelectArgs a) {
 // --------------------------------------------------------------------------------------------
 struct MergeArgs {
   const int32_t *core, *mem, *mem_total;
-  RoundSet set;
+  const RoundDesc *rd;
   TableSet tb;
   uint8_t *obs_pending;
   const unsigned long long *cta_lists; const AggPart *cta_agg; int n_cta;
-  ShardBuf *out;
+  char *out; BufLayout L;           // this shard's candidate buffer
+  const RoundCtl *ctl;
 };
 
 __global__ void __launch_bounds__(256) k_merge(MergeArgs a) {
-  __shared__ unsigned long long s_l[8][RK];
+  __shared__ unsigned long long s_l[8][RQMAX * 32];
   __shared__ AggPart s_a[8];
-  __shared__ unsigned long long s_final[RK];
+  __shared__ unsigned long long s_floor[8];
+  __shared__ unsigned long long s_final[RQMAX * 32];
+  __shared__ int s_len;
+  if (ctl_idle(a.ctl)) return;
   const int s = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  unsigned long long L = 0;
+  const int ns = a.rd->ns, nsc = a.L.nsc;
+  unsigned long long A[RQMAX] = {0, 0, 0, 0};
+  unsigned long long floor_k = 0;    // the merged list is exact down to the largest LAST key of a full CTA list
   AggPart ag; ag.fd = 0; ag.sd = 0; ag.fit = 0; ag.pad = 0;
   for (int c = warp; c < a.n_cta; c += 8) {
-    L = merge_top32(L, a.cta_lists[((size_t)c * RS + s) * RK + lane], lane);
-    if (lane == 0) { const AggPart p = a.cta_agg[(size_t)c * RS + s]; ag.fd += p.fd; ag.sd += p.sd; ag.fit += p.fit; }
+    const unsigned long long b = a.cta_lists[((size_t)c * nsc + s) * RK + lane];
+    const unsigned long long last = __shfl_sync(0xffffffffu, b, 31);
+    floor_k = last > floor_k ? last : floor_k;
+    merge32_into128(A, b, lane);
+    if (lane == 0) { const AggPart p = a.cta_agg[(size_t)c * nsc + s]; ag.fd += p.fd; ag.sd += p.sd; ag.fit += p.fit; }
   }
-  if (lane < RK) s_l[warp][lane] = L;
-  if (lane == 0) s_a[warp] = ag;
+#pragma unroll
+  for (int q = 0; q < RQMAX; q++) s_l[warp][q * 32 + lane] = A[q];
+  if (lane == 0) { s_a[warp] = ag; s_floor[warp] = floor_k; }
   __syncthreads();
   if (warp == 0) {
-    L = s_l[0][lane];
-    for (int w = 1; w < 8; w++) L = merge_top32(L, s_l[w][lane], lane);
-    if (lane < RK) s_final[lane] = L;
+    for (int w = 1; w < 8; w++) {
+      unsigned long long B[RQMAX];
+#pragma unroll
+      for (int q = 0; q < RQMAX; q++) B[q] = s_l[w][q * 32 + lane];
+      merge128(A, B, lane);
+      floor_k = s_floor[w] > floor_k ? s_floor[w] : floor_k;
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int q = 0; q < RQMAX; q++) {
+      s_final[q * 32 + lane] = A[q];
+      cnt += __popc(__ballot_sync(0xffffffffu, A[q] != 0 && A[q] >= floor_k));
+    }
     if (lane == 0) {
       AggPart t = s_a[0];
       for (int w = 1; w < 8; w++) { t.fd += s_a[w].fd; t.sd += s_a[w].sd; t.fit += s_a[w].fit; }
-      const int len = t.fit < RK ? t.fit : RK;
-      a.out->len[s] = len; a.out->more[s] = t.fit > RK; a.out->fit[s] = t.fit; a.out->fd[s] = t.fd; a.out->sd[s] = t.sd;
-      a.obs_pending[a.set.slot[s]] = 0;                        // consumed by this round's select
+      const int len = cnt < a.L.rkm ? cnt : a.L.rkm;
+      s_len = len;
+      reinterpret_cast<int *>(a.out + a.L.off_len)[s] = len;
+      reinterpret_cast<int *>(a.out + a.L.off_more)[s] = t.fit > len;
+      reinterpret_cast<int *>(a.out + a.L.off_fit)[s] = t.fit;
+      reinterpret_cast<unsigned long long *>(a.out + a.L.off_fd)[s] = t.fd;
+      reinterpret_cast<unsigned long long *>(a.out + a.L.off_sd)[s] = t.sd;
+      a.obs_pending[a.rd->slot[s]] = 0;                        // consumed by this round's select
     }
   }
   __syncthreads();
   // payload: 16 threads per candidate, 16 candidates per pass
-  for (int k = threadIdx.x >> 4; k < RK; k += 16) {
+  const int len = s_len;
+  for (int k = threadIdx.x >> 4; k < a.L.rkm; k += 16) {
     const int f = threadIdx.x & 15;
+    char *cd = a.out + a.L.off_cand + ((size_t)s * a.L.rkm + k) * a.L.cand_bytes;
+    if (k >= len) { if (f == 0) *reinterpret_cast<unsigned long long *>(cd + CD_KEY) = 0; continue; }
     const unsigned long long key = s_final[k];
-    Cand *cd = &a.out->cand[s][k];
-    if (key == 0) { if (f == 0) cd->key = 0; continue; }
     const size_t node = key_node(key);
-    if (f == 0) { cd->key = key; cd->mt = a.mem_total[node]; cd->pad = 0; }
-    if (f == 1) cd->fterm = fit_term((uint32_t)node);
-    if (f == 2) cd->sbase = score_base((uint32_t)node);
-    if (f < EGS_G) cd->rc[f] = a.core[node * EGS_G + f]; else cd->rm[f - EGS_G] = a.mem[node * EGS_G + f - EGS_G];
-    for (int s2 = f; s2 < RS; s2 += 16) {
+    if (f == 0) { *reinterpret_cast<unsigned long long *>(cd + CD_KEY) = key; *reinterpret_cast<int *>(cd + CD_MT) = a.mem_total[node]; *reinterpret_cast<int *>(cd + CD_MT + 4) = 0; }
+    if (f == 1) *reinterpret_cast<unsigned long long *>(cd + CD_FT) = fit_term((uint32_t)node);
+    if (f == 2) *reinterpret_cast<unsigned long long *>(cd + CD_SB) = score_base((uint32_t)node);
+    if (f < EGS_G) reinterpret_cast<int *>(cd + CD_RC)[f] = a.core[node * EGS_G + f];
+    else reinterpret_cast<int *>(cd + CD_RM)[f - EGS_G] = a.mem[node * EGS_G + f - EGS_G];
+    int *csc = reinterpret_cast<int *>(cd + CD_SC);
+    uint32_t *cal = reinterpret_cast<uint32_t *>(cd + CD_SC + 4 * nsc);
+    uint8_t *cst = reinterpret_cast<uint8_t *>(cd + CD_SC + 8 * nsc);
+    for (int s2 = f; s2 < nsc; s2 += 16) {
       uint8_t st = OPT_UNFIT; int32_t sc = 0; uint32_t al = 0;
-      if (s2 < a.set.n) {
-        const int slot = a.set.slot[s2];
+      if (s2 < ns) {
+        const int slot = a.rd->slot[s2];
         st = tb_st(a.tb, slot)[node]; sc = tb_sc(a.tb, slot)[node];
         const uint8_t *alp = tb_al(a.tb, slot);
         for (int c = 0; c < EGS_C; c++) al |= (uint32_t)alp[(size_t)c * a.tb.n_pad + node] << (8 * c);
       }
-      cd->st[s2] = st; cd->sc[s2] = sc; cd->al[s2] = al;
+      cst[s2] = st; csc[s2] = sc; cal[s2] = al;
     }
   }
 }
 
 // --------------------------------------------------------------------------------------------
-// k_resolve: one warp
+// k_resolve_mw: one CTA, one owner warp per shape (shape index si is owned by warp si % nw)
 // --------------------------------------------------------------------------------------------
-struct ResolveArgs {
+struct MwArgs {
   int32_t *core, *mem;              // write-back targets
   int lo, hi, policy, n_shards;
-  RoundSet set;
-  Req reqs[RS];
+  const RoundDesc *rd;
   TableSet tb;
   uint8_t *obs_pending;
-  const ShardBuf *bufs;             // [n_shards]
-  const int32_t *pod_slot; int p0, p_limit;
+  const char *bufs; BufLayout L;    // [n_shards] candidate buffers
+  const uint8_t *pod_sidx;          // per pod: index of its shape in the round set
+  int p0, p_limit;                  // p0 < 0: pods [ctl->next_p, ctl->p_end)
   PodOut out;
-  int32_t *done;                    // [0] pods resolved, [1] tracked nodes, [2] stop reason
-  long long *prof;                  // EGS_RESOLVE_PROF: 12 counters
+  RoundCtl *ctl;
+  int rke;                          // list entries per (shape, shard) held in shared memory
+  int nw;                           // worker warps
 };
 
-#define RTW (RT / 32)
-struct ResolveSmem {                 // shape-major, padded: lanes = tracked slots OR lanes = shapes are both conflict-free
-  unsigned long long lkey[RS][RD * RK];   // untracked candidate lists (sorted, consumed entries zeroed)
-  unsigned long long tkey[RS][RT];        // cand_key of a tracked node's option when it is fit (CACHED/NEW), else 0
-  uint32_t al[RS][RT + 1];                // option.Allocated masks
-  uint8_t st[RS][RT + 4];                 // OPT_*
-  unsigned pmask[RS][RTW];                // tracked slots whose option is ABSENT: Trade at the shape's next pod
-  unsigned long long hkey[RS][RD];        // current head of each list (0 = none)
-  unsigned long long afd[RS], asd[RS];
-  int afit[RS];
-  int cur[RS][RD], len[RS][RD], more[RS][RD];
-  int observed[RS];
-  int rq_single[RS], rq_core[RS], rq_mem[RS]; uint32_t rq_cmask[RS];
-  int node[RT], mt[RT], dirty[RT];
-  unsigned long long fterm[RT];           // fit_term(node) of each tracked slot
-  unsigned long long sbase[RT];           // score_base(node) of each tracked slot
-  int rc[RT][EGS_G], rm[RT][EGS_G];
-  // per-pod outputs, flushed 32 pods at a time with coalesced stores
-  int o_node[64], o_status[64], o_fit[64]; uint32_t o_alloc[64]; unsigned long long o_fd[64], o_sd[64];
-  int8_t set_idx[2048];                   // option-table slot id -> index in the round's shape set (-1: not in it)
-  Req reqs[RS];
-  int hset[512];                          // open-addressed set of tracked node ids (-1 empty): lazy list maintenance
-  int hpay_node[RS];                      // node whose payload sits (or is arriving) in hpay[s]; -1 none
-  alignas(16) Cand hpay[RS];              // prefetched payload of each shape's best untracked head
+template <int NS, int NT>
+struct MwSmem {
+  static constexpr int HS = 2 * NT;                        // open-addressed set of tracked node ids
+  unsigned long long tkey[NS][NT];   // cand_key of a tracked node's option when it is fit (CACHED/NEW), else 0
+  unsigned long long hkey[NS][RD];   // current head of each untracked list (0 = none)
+  unsigned long long afd[NS], asd[NS], bh[NS];             // aggregates; best head over the shards
+  unsigned long long fterm[NT], sbase[NT];                 // fit_term / score_base of each tracked slot's node
+  uint32_t al[NS][NT];               // option.Allocated masks
+  unsigned pmask[NS][NT / 32];       // tracked slots whose option is ABSENT: Trade at the shape's next pod
+  int afit[NS], bh_d[NS], dry[NS], observed[NS];
+  int pu[NS];                        // summary of pmask[s]: -1 none, t >= 0 exactly slot t, -2 unknown / several
+  int rq_single[NS], rq_core[NS], rq_mem[NS]; uint32_t rq_cmask[NS];
+  int node[NT], mt[NT], dirty[NT];
+  int rc[NT][EGS_G], rm[NT][EGS_G];
+  int hset[HS];
+  Req reqs[NS];
+  uint8_t st[NS][NT];                // OPT_*
+  uint8_t cur[NS][RD], len[NS][RD], more[NS][RD];
+  int turn, stop, stop_reason, nT, n_observed, mono, p0, p_end;
 };
 
-__device__ __forceinline__ unsigned hset_slot(uint32_t node) { return (node * 2654435761u) >> 23; }   // 9 bits
-__device__ __forceinline__ bool hset_has(const ResolveSmem &S, uint32_t node) {
-  for (unsigned i = hset_slot(node);; i = (i + 1) & 511u) {
+__device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
+__device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+
+template <class SM>
+__device__ __forceinline__ unsigned hset_slot(uint32_t node) {
+  return ((node * 2654435761u) >> 8) & (unsigned)(SM::HS - 1);
+}
+template <class SM>
+__device__ __forceinline__ bool hset_has(const SM &S, uint32_t node) {
+  for (unsigned i = hset_slot<SM>(node);; i = (i + 1) & (unsigned)(SM::HS - 1)) {
     const int v = S.hset[i];
     if (v == (int)node) return true;
     if (v < 0) return false;
   }
 }
-__device__ __forceinline__ void hset_add(ResolveSmem &S, uint32_t node) {   // one lane; at most RT (256) entries
-  unsigned i = hset_slot(node);
-  while (S.hset[i] >= 0) i = (i + 1) & 511u;
+template <class SM>
+__device__ __forceinline__ void hset_add(SM &S, uint32_t node) {   // one lane; at most NT entries (load <= 1/2)
+  unsigned i = hset_slot<SM>(node);
+  while (S.hset[i] >= 0) i = (i + 1) & (unsigned)(SM::HS - 1);
   S.hset[i] = (int)node;
 }
 // advance list (s, d) past entries whose node is tracked by now, and cache its head
-__device__ __forceinline__ void list_head_update(ResolveSmem &S, int s, int d) {
+template <class SM>
+__device__ __forceinline__ void list_head_update(SM &S, const unsigned long long *lk, int D, int rke, int s, int d) {
   int c = S.cur[s][d];
   const int len = S.len[s][d];
   unsigned long long k = 0;
-  while (c < len) { k = S.lkey[s][d * RK + c]; if (!hset_has(S, key_node(k))) break; c++; }
-  S.cur[s][d] = c;
+  const unsigned long long *l = lk + ((size_t)s * D + d) * rke;
+  while (c < len) { k = l[c]; if (!hset_has(S, key_node(k))) break; c++; }
+  S.cur[s][d] = (uint8_t)c;
   S.hkey[s][d] = c < len ? k : 0ull;
 }
-
-// pods [p_first, p_first + n), n <= 32, sit in ring entries (rel0 + i) & 63
-__device__ __forceinline__ void flush_outputs(const ResolveSmem &S, const PodOut &out, int p_first, int rel0, int n, int lane) {
-  if (lane < n) {
-    const size_t p = (size_t)p_first + lane;
-    const int r = (rel0 + lane) & 63;
-    if (out.node) out.node[p] = S.o_node[r];
-    if (out.status) out.status[p] = S.o_status[r];
-    if (out.fit_count) out.fit_count[p] = S.o_fit[r];
-    if (out.fit_digest) out.fit_digest[p] = S.o_fd[r];
-    if (out.score_digest) out.score_digest[p] = S.o_sd[r];
-    if (out.alloc) reinterpret_cast<uint32_t *>(out.alloc)[p] = S.o_alloc[r];
+// best head of shape s over the shards, and whether a truncated list ran dry (one lane)
+template <class SM>
+__device__ __forceinline__ void best_head_update(SM &S, int D, int s) {
+  unsigned long long b = 0; int bd = 0, dry = 0;
+  for (int d = 0; d < D; d++) {
+    const unsigned long long k = S.hkey[s][d];
+    if (k > b) { b = k; bd = d; }
+    dry |= (k == 0 && S.more[s][d] != 0);
   }
+  S.bh[s] = b; S.bh_d[s] = bd; S.dry[s] = dry;
 }
 
 #ifdef EGS_RESOLVE_PROF
 #define PROF_T(i) { long long now_ = clock64(); prof[i] += now_ - tprev; tprev = now_; }
 #define PROF_C(i, v) { prof[i] += (v); }
-#define PROF_PTR prof
 #else
 #define PROF_T(i)
 #define PROF_C(i, v)
-#define PROF_PTR nullptr
 #endif
-// Segmented (8-lane group) reductions with FULL-mask shuffles: xor offsets 1,2,4 never leave a group,
-// so all four groups reduce at once.  (Collectives with a different member mask per group are issued
-// one group at a time by the hardware.)
-__device__ __forceinline__ int seg8_max(int v) {
-  v = max(v, __shfl_xor_sync(0xffffffffu, v, 1)); v = max(v, __shfl_xor_sync(0xffffffffu, v, 2));
-  return max(v, __shfl_xor_sync(0xffffffffu, v, 4));
-}
-__device__ __forceinline__ unsigned seg8_minu(unsigned v) {
-  v = min(v, __shfl_xor_sync(0xffffffffu, v, 1)); v = min(v, __shfl_xor_sync(0xffffffffu, v, 2));
-  return min(v, __shfl_xor_sync(0xffffffffu, v, 4));
-}
-__device__ __forceinline__ int seg8_add(int v) {
-  v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2);
-  return v + __shfl_xor_sync(0xffffffffu, v, 4);
-}
-__device__ __forceinline__ unsigned long long seg8_max64(unsigned long long v) {
-#pragma unroll
-  for (int o = 1; o < 8; o <<= 1) { const unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o); v = x > v ? x : v; }
-  return v;
+
+__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long mine, int &owner_lane) {
+  // max of a 64-bit key over the warp: two redux.sync steps on the halves; owner = lowest lane holding it
+  const unsigned hi = (unsigned)(mine >> 32);
+  const unsigned m1 = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned m2 = __reduce_max_sync(0xffffffffu, hi == m1 ? (unsigned)mine : 0u);
+  const unsigned long long win = ((unsigned long long)m1 << 32) | m2;
+  owner_lane = __ffs(__ballot_sync(0xffffffffu, mine == win)) - 1;
+  return win;
 }
 
-// Best untracked head of shape s over the shards -> (key, shard); warp-uniform result.
-__device__ __forceinline__ unsigned long long best_head(const ResolveSmem &S, int s, int D, int &d_out) {
-  unsigned long long b = 0; int bd = 0;
-  for (int d = 0; d < D; d++) { const unsigned long long k = S.hkey[s][d]; if (k > b) { b = k; bd = d; } }
-  d_out = bd;
-  return b;
-}
-// Start the asynchronous copy of that head's payload into S.hpay[s] (23 x 16 B, one chunk per lane).
-__device__ __forceinline__ void prefetch_head(ResolveSmem &S, const ResolveArgs &a, int s, int D, int lane) {
-  int d; const unsigned long long k = best_head(S, s, D, d);
-  if (k == 0) { if (lane == 0) S.hpay_node[s] = -1; return; }
-  const char *src = reinterpret_cast<const char *>(&a.bufs[d].cand[s][S.cur[s][d]]);
-  if (lane < (int)(sizeof(Cand) / 16)) {
-    const unsigned dst = (unsigned)__cvta_generic_to_shared(reinterpret_cast<char *>(&S.hpay[s]) + lane * 16);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + lane * 16));
+// Trade of one fractional single-container request on a tracked node, one lane per GPU (lane & 7), every
+// lane holding the whole row: no shuffles until the final max.  Returns the folded key q*8+g (-1: no fit).
+__device__ __forceinline__ int trade_lanes(const int (&c)[EGS_G], const int (&m)[EGS_G], int gl, int rq_c, int rq_m, int policy) {
+  unsigned ucmin = 0xFFFFFFFFu, ummin = 0xFFFFFFFFu;
+  int cex = INT32_MIN, mex = INT32_MIN, cg = 0, mg = 0;
+#pragma unroll
+  for (int g = 0; g < EGS_G; g++) {
+    ucmin = min(ucmin, (unsigned)c[g]); ummin = min(ummin, (unsigned)m[g]);
+    cex = max(cex, g == gl ? INT32_MIN : c[g]); mex = max(mex, g == gl ? INT32_MIN : m[g]);
+    cg = g == gl ? c[g] : cg; mg = g == gl ? m[g] : mg;
   }
-  if (lane == 0) S.hpay_node[s] = (int)key_node(k);
+  const bool ok = cg >= rq_c && mg >= rq_m;                      // CanAllocate gpu.go:55; PAD rows fail
+  const int nc = cg - rq_c, nm = mg - rq_m;                      // GPU.Add gpu.go:36-37
+  const int x = (max(mex, nm) + max(cex, nc)) - (min((int)ummin, nm) + min((int)ucmin, nc));
+  const int key = !ok ? -1 : (policy == EGS_BINPACK ? (x >> 2) * 8 + gl : gl);
+  return __reduce_max_sync(0xffffffffu, key);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-struct PodRec {                     // decision of one pod, made by an 8-lane group (fast path)
-  int s, u, bk, from_head, t, d, fit, pad;
-  unsigned long long win, fd, sd;
-};
+// A slot becomes tracked: install the payload of candidate `cd` (node w) as tracked slot t.  All lanes.
+template <class SM>
+__device__ __forceinline__ void install_slot(SM &S, const MwArgs &a, const char *cd, int t, uint32_t w, int ns, int lane) {
+  const int nsc = a.L.nsc;
+  if (lane < 2 * EGS_G) {
+    const int v = reinterpret_cast<const int *>(cd + CD_RC)[lane];          // rc[8], rm[8] contiguous
+    if (lane < EGS_G) S.rc[t][lane] = v; else S.rm[t][lane - EGS_G] = v;
+  }
+  if (lane == 0) {
+    S.node[t] = (int)w; S.mt[t] = *reinterpret_cast<const int *>(cd + CD_MT); S.dirty[t] = 0;
+    S.fterm[t] = *reinterpret_cast<const unsigned long long *>(cd + CD_FT);
+    S.sbase[t] = *reinterpret_cast<const unsigned long long *>(cd + CD_SB);
+    hset_add(S, w);
+  }
+  const int *csc = reinterpret_cast<const int *>(cd + CD_SC);
+  const uint32_t *cal = reinterpret_cast<const uint32_t *>(cd + CD_SC + 4 * nsc);
+  const uint8_t *cst = reinterpret_cast<const uint8_t *>(cd + CD_SC + 8 * nsc);
+  for (int s2 = lane; s2 < ns; s2 += 32) {
+    uint8_t st = cst[s2];
+    if (st == OPT_NEW && S.observed[s2]) st = OPT_CACHED;
+    S.st[s2][t] = st; S.al[s2][t] = cal[s2];
+    S.tkey[s2][t] = (st == OPT_CACHED || st == OPT_NEW) ? cand_key(csc[s2], w) : 0ull;
+    if (st == OPT_ABSENT) { atomicOr(&S.pmask[s2][t >> 5], 1u << (t & 31)); S.pu[s2] = -2; }   // select leaves none; kept for safety
+  }
+}
 
-// Commit of one decided pod: NodeAllocator.Allocate (node.go:87-104) on the tracked copy, or NOFIT.
-// (fitc, ofd, osd) are the shape's aggregates after this pod's filter; warp-uniform arguments.
-__device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a, int lane, int rel, int s,
-                                           unsigned long long win, int from_head, int t_in, int d, int fitc,
-                                           unsigned long long ofd, unsigned long long osd, bool mono, int ns, int D,
-                                           int &nT, int n_observed, long long *prof) {
-#ifdef EGS_RESOLVE_PROF
-  long long tprev = clock64();
-#endif
-  int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
-  if (win != 0) {
-    int t = t_in;
-    if (from_head) {
-      // an untracked node wins: it becomes tracked.  Its payload was prefetched into shared memory when it
-      // became the best head of this shape (cp.async); fall back to the candidate buffer otherwise.
-      t = nT++;
-      const uint32_t w = key_node(win);
-      cp_async_wait_all();
-      __syncwarp();
-      PROF_T(12)
-      {
-        int rowv, mtv, scv; uint32_t alv; uint8_t st; unsigned long long ft, sb;
-        if (S.hpay_node[s] == (int)w) {                            // warp-uniform: payload already in shared memory
-          const Cand &cd = S.hpay[s];
-          rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0; mtv = cd.mt; st = cd.st[lane]; scv = cd.sc[lane]; alv = cd.al[lane]; ft = cd.fterm; sb = cd.sbase;
-        } else {
-          const Cand &cd = a.bufs[d].cand[s][S.cur[s][d]];
-          rowv = lane < 2 * EGS_G ? cd.rc[lane] : 0; mtv = cd.mt; st = cd.st[lane]; scv = cd.sc[lane]; alv = cd.al[lane]; ft = cd.fterm; sb = cd.sbase;
-        }
-        if (lane < EGS_G) S.rc[t][lane] = rowv; else if (lane < 2 * EGS_G) S.rm[t][lane - EGS_G] = rowv;   // rc[8], rm[8] contiguous
-        if (lane == 0) { S.node[t] = (int)w; S.mt[t] = mtv; S.dirty[t] = 0; S.fterm[t] = ft; S.sbase[t] = sb; hset_add(S, w); }
-        if (st == OPT_NEW && S.observed[lane]) st = OPT_CACHED;   // lane == shape index
-        S.st[lane][t] = st; S.al[lane][t] = alv;
-        S.tkey[lane][t] = (st == OPT_CACHED || st == OPT_NEW) ? cand_key(scv, w) : 0ull;
-        if (st == OPT_ABSENT) S.pmask[lane][t >> 5] |= 1u << (t & 31);
-      }
-      __syncwarp();
-      PROF_T(13)
-      // it leaves the untracked lists lazily: only lists whose HEAD is this node advance now (entries deeper
-      // in a list are skipped when they surface); then the changed heads get their payloads prefetched
-      for (int i = lane; i < ns * D; i += 32) {
-        const unsigned long long hk = S.hkey[i / D][i % D];
-        if (hk != 0 && key_node(hk) == w) list_head_update(S, i / D, i % D);
-      }
-      __syncwarp();
-      PROF_T(14)
-      if (lane < ns) {                                            // lane == shape: its own 23 x 16 B copies, in lockstep
-        int dd; const unsigned long long k = best_head(S, lane, D, dd);
-        const int want = k ? (int)key_node(k) : -1;
-        if (want != S.hpay_node[lane]) {
-          S.hpay_node[lane] = want;
-          if (k) {
-            const char *src = reinterpret_cast<const char *>(&a.bufs[dd].cand[lane][S.cur[lane][dd]]);
-            const unsigned dst = (unsigned)__cvta_generic_to_shared(&S.hpay[lane]);
+// the lists whose HEAD is node w advance now (entries deeper in a list are skipped when they surface)
+template <class SM>
+__device__ __forceinline__ void heads_drop_node(SM &S, const unsigned long long *lk, int D, int rke, int ns, uint32_t w, int lane) {
+  for (int i = lane; i < ns * D; i += 32) {
+    const int s2 = i / D, d2 = i % D;
+    const unsigned long long hk = S.hkey[s2][d2];
+    if (hk != 0 && key_node(hk) == w) list_head_update(S, lk, D, rke, s2, d2);
+  }
+  __syncwarp();
+  for (int s2 = lane; s2 < ns; s2 += 32) best_head_update(S, D, s2);
+}
+
+// ---- general pod (inside the ticket, whole warp): any shape, any number of pending options, any regime.
+// Returns 0, or the stop reason (nothing was changed for this pod then).
+template <class SM>
+__device__ int general_pod(SM &S, const MwArgs &a, const unsigned long long *lk, int lane, int p, int s, int ns, int D, int rke) {
+  const int grp = lane >> 3, gl = lane & 7;
+  const unsigned gmask = 0xFFu << (8 * grp);
+  const bool mono = S.mono != 0;
+  int nT = S.nT;
+  if (nT >= SM::HS / 2) return 2;                               // no free tracked slot for a new winner
+  if (S.dry[s]) return 3;                                       // a truncated list ran dry: next round
+  if (!S.observed[s]) {                                         // first pod of this shape in the round:
+    for (int t = lane; t < nT; t += 32) if (S.st[s][t] == OPT_NEW) S.st[s][t] = OPT_CACHED;   // NEW options are now ordinary
+    __syncwarp();
+    if (lane == 0) { S.observed[s] = 1; S.n_observed = S.n_observed + 1; }
+    __syncwarp();
+  }
+  const int single = S.rq_single[s];
+  // tracked nodes: Trade absent options NOW (this pod's filter); best tracked option
+  unsigned long long best = 0; int best_t = -1;
+  const int nwords = (nT + 31) >> 5;
+  for (int w = 0; w < nwords; w++) {
+    unsigned word = S.pmask[s][w];
+    if (word) {
+      if (single) {
+        // 8 lanes per pending node (lane == GPU), up to 4 nodes at a time
+        const int rq_c = S.rq_core[s], rq_m = S.rq_mem[s];
+        while (word) {
+          int bsel = -1;
 #pragma unroll
-            for (int q = 0; q < (int)(sizeof(Cand) / 16); q++)
-              asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + q * 16), "l"(src + q * 16));
+          for (int q = 0; q < 4; q++) {
+            const int b = word ? __ffs(word) - 1 : -1;
+            if (word) word &= word - 1;
+            if (q == grp) bsel = b;
+          }
+          bool okl = false; int sc = 0; int t = 0;
+          if (bsel >= 0) {                                       // group-uniform
+            t = w * 32 + bsel;
+            const int c = S.rc[t][gl], m = S.rm[t][gl];
+            const int cmin = (int)__reduce_min_sync(gmask, (unsigned)c), mmin = (int)__reduce_min_sync(gmask, (unsigned)m);
+            const int c1 = __reduce_max_sync(gmask, c), m1 = __reduce_max_sync(gmask, m);
+            const int c2 = __reduce_max_sync(gmask, c == c1 ? INT32_MIN : c), m2 = __reduce_max_sync(gmask, m == m1 ? INT32_MIN : m);
+            const bool cu = __popc(__ballot_sync(gmask, c == c1)) == 1, mu = __popc(__ballot_sync(gmask, m == m1)) == 1;
+            const int cex = (c == c1 && cu) ? c2 : c1, mex = (m == m1 && mu) ? m2 : m1;   // max over the OTHER GPUs
+            const bool ok = c >= rq_c && m >= rq_m;                                         // gpu.go:55
+            const int nc = c - rq_c, nm = m - rq_m;
+            const int x = (max(mex, nm) + max(cex, nc)) - (min(mmin, nm) + min(cmin, nc));
+            const int key = !ok ? -1 : (a.policy == EGS_BINPACK ? (x >> 2) * 8 + gl : gl);
+            const int bk = __reduce_max_sync(gmask, key);
+            if (gl == 0) {
+              if (bk >= 0) {
+                sc = a.policy == EGS_BINPACK ? (bk >> 3) * 100 : 0;
+                S.st[s][t] = OPT_CACHED; S.al[s][t] = 1u << (bk & 7); S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]);
+                okl = true;
+              } else {
+                S.st[s][t] = OPT_UNFIT;
+              }
+            }
+          }
+          for (unsigned rem = __ballot_sync(0xffffffffu, okl); rem; rem &= rem - 1) {   // usually one leader
+            if (lane == __ffs(rem) - 1) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term_b(S.sbase[t], sc); }
+            __syncwarp();
           }
         }
+      } else {
+        const int t = w * 32 + lane;
+        bool ok = false; int sc = 0;
+        if ((word >> lane) & 1u) {
+          uint32_t masks;
+          ok = trade_general(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], a.policy, sc, masks);
+          if (ok) { S.st[s][t] = OPT_CACHED; S.al[s][t] = masks; S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]); }
+          else S.st[s][t] = OPT_UNFIT;
+        }
+        for (unsigned rem = word; rem; rem &= rem - 1) {
+          if (lane == __ffs(rem) - 1 && ok) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term_b(S.sbase[t], sc); }
+          __syncwarp();
+        }
       }
-      cp_async_commit();
-      PROF_T(15) PROF_C(11, 1)
+      __syncwarp();
+      if (lane == 0) S.pmask[s][w] = 0;
+    }
+    const int t = w * 32 + lane;
+    const unsigned long long k = t < nT ? S.tkey[s][t] : 0ull;
+    if (k > best) { best = k; best_t = t; }
+  }
+  __syncwarp();
+  // winner = max over (tracked options, best untracked list head)
+  int owner;
+  const unsigned long long tbest = warp_max_key(best, owner);
+  const int tw0 = __shfl_sync(0xffffffffu, best_t, owner);
+  const unsigned long long head = S.bh[s];
+  const bool from_head = head > tbest;
+  const unsigned long long win = from_head ? head : tbest;
+  const int fitc = S.afit[s];
+  const unsigned long long ofd = S.afd[s], osd = S.asd[s];
+  // ---- commit: NodeAllocator.Allocate (node.go:87-104) on the tracked copy, or NOFIT
+  int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
+  int pu_new = -1;
+  if (win != 0) {
+    int t = tw0;
+    if (from_head) {
+      // an untracked node wins: it becomes tracked
+      t = nT;
+      const uint32_t w = key_node(win);
+      const int d = S.bh_d[s];
+      const char *cd = a.bufs + (size_t)d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + S.cur[s][d]) * a.L.cand_bytes;
+      install_slot(S, a, cd, t, w, ns, lane);
+      __syncwarp();
+      heads_drop_node(S, lk, D, rke, ns, w, lane);
+      __syncwarp();
+      nT = t + 1;
+      if (lane == 0) { __threadfence_block(); S.nT = nT; }
     }
     o_node = S.node[t];
-    const int single = S.rq_single[s];
     const uint32_t masks = S.al[s][t] & S.rq_cmask[s];
     const unsigned pbit = 1u << (t & 31);
     int ok = 0;
-    // deferred delete of the option (node.go:90-92) + aggregates: computed by every lane (broadcast loads),
-    // stored by lane 0 -- no divergent region on the common single-container path
+    // deferred delete of the option (node.go:90-92) + aggregates
     const int nfit = fitc - 1;
     const unsigned long long nfd = ofd - S.fterm[t], nsd = osd - score_term_b(S.sbase[t], key_score(win));
     const unsigned npm = S.pmask[s][t >> 5] | pbit;
@@ -476,16 +651,20 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
       }
       ok = __shfl_sync(0xffffffffu, ok, 0);
     }
+    pu_new = t;
     // Rows changed.  (a) not-yet-observed NEW options of this node are void (only while some shape of the
     // round is unobserved); (b) UNFIT memos are void -- unless every request of the round is >= 0: rows
     // then only decrease and an option that did not fit can never fit (exact shortcut).
-    if ((!mono || n_observed < ns) && lane < ns && lane != s) {
-      const uint8_t v = S.st[lane][t];
-      if (v == OPT_UNFIT && !mono) { S.st[lane][t] = OPT_ABSENT; S.pmask[lane][t >> 5] |= pbit; }
-      else if (v == OPT_NEW && !S.observed[lane]) {
-        const unsigned long long k2 = S.tkey[lane][t];
-        S.st[lane][t] = OPT_ABSENT; S.tkey[lane][t] = 0; S.pmask[lane][t >> 5] |= pbit;
-        S.afit[lane] -= 1; S.afd[lane] -= S.fterm[t]; S.asd[lane] -= score_term_b(S.sbase[t], key_score(k2));
+    if (!mono || S.n_observed < ns) {
+      for (int s2 = lane; s2 < ns; s2 += 32) {
+        if (s2 == s) continue;
+        const uint8_t v = S.st[s2][t];
+        if (v == OPT_UNFIT && !mono) { S.st[s2][t] = OPT_ABSENT; S.pmask[s2][t >> 5] |= pbit; S.pu[s2] = -2; }
+        else if (v == OPT_NEW && !S.observed[s2]) {
+          const unsigned long long k2 = S.tkey[s2][t];
+          S.st[s2][t] = OPT_ABSENT; S.tkey[s2][t] = 0; S.pmask[s2][t >> 5] |= pbit; S.pu[s2] = -2;
+          S.afit[s2] -= 1; S.afd[s2] -= S.fterm[t]; S.asd[s2] -= score_term_b(S.sbase[t], key_score(k2));
+        }
       }
     }
     __syncwarp();
@@ -493,361 +672,300 @@ __device__ __forceinline__ void commit_pod(ResolveSmem &S, const ResolveArgs &a,
     o_masks = ok ? masks : 0;
   }
   if (lane == 0) {
-    const int r = rel & 63;
-    S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fitc; S.o_fd[r] = ofd; S.o_sd[r] = osd; S.o_alloc[r] = o_masks;
+    S.pu[s] = pu_new;                                           // every pending option of s was Traded above
+    if (a.out.node) a.out.node[p] = o_node;
+    if (a.out.status) a.out.status[p] = o_status;
+    if (a.out.fit_count) a.out.fit_count[p] = fitc;
+    if (a.out.fit_digest) a.out.fit_digest[p] = ofd;
+    if (a.out.score_digest) a.out.score_digest[p] = osd;
+    if (a.out.alloc) reinterpret_cast<uint32_t *>(a.out.alloc)[p] = o_masks;
   }
   __syncwarp();
+  return 0;
 }
 
-__global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
+template <int NS, int NT>
+__global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ResolveSmem &S = *reinterpret_cast<ResolveSmem *>(smem_raw);
-  __shared__ PodRec recs[4];
-  const int lane = threadIdx.x;
-  const int D = a.n_shards, ns = a.set.n, DK = D * RK;
-  const int grp = lane >> 3, gl = lane & 7;                      // 8-lane groups: one lane per GPU of a node
-  const unsigned gmask = 0xFFu << (8 * grp);
+  using SM = MwSmem<NS, NT>;
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  unsigned long long *lk = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15));   // [ns][D][rke]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const int D = a.n_shards, rke = a.rke, nw = a.nw;
+  const int ns = a.rd->ns;
   // ---- prologue
-  for (int i = lane; i < 512; i += 32) S.hset[i] = -1;
-  bool mono = true;                                              // all requests >= 0: rows only decrease in this round
   {
-    const int s = lane;                                          // RS == 32: one shape per lane
+    int p0 = a.p0, p_end = a.p_limit;
+    if (a.p0 < 0) { if (ctl_idle(a.ctl)) return; p0 = a.ctl->next_p; p_end = a.ctl->p_end; }
+    if (tid == 0) { S.p0 = p0; S.p_end = p_end; S.turn = p0; S.stop = 0; S.stop_reason = 0; S.nT = 0; S.n_observed = 0; }
+  }
+  for (int i = tid; i < SM::HS; i += nthreads) S.hset[i] = -1;
+  for (int i = tid; i < NS * (NT / 32); i += nthreads) (&S.pmask[0][0])[i] = 0;
+  for (int s = tid; s < NS; s += nthreads) {
     int fit = 0; unsigned long long fd = 0, sd = 0;
     for (int d = 0; d < D; d++) {
-      const ShardBuf &b = a.bufs[d];
-      S.cur[s][d] = 0; S.len[s][d] = s < ns ? b.len[s] : 0; S.more[s][d] = s < ns ? b.more[s] : 0;
-      if (s < ns) { fit += b.fit[s]; fd += b.fd[s]; sd += b.sd[s]; }
+      const char *b = a.bufs + (size_t)d * a.L.bytes;
+      int len = 0, more = 0;
+      if (s < ns) {
+        len = reinterpret_cast<const int *>(b + a.L.off_len)[s];
+        more = reinterpret_cast<const int *>(b + a.L.off_more)[s];
+        fit += reinterpret_cast<const int *>(b + a.L.off_fit)[s];
+        fd += reinterpret_cast<const unsigned long long *>(b + a.L.off_fd)[s];
+        sd += reinterpret_cast<const unsigned long long *>(b + a.L.off_sd)[s];
+        if (len > rke) { len = rke; more = 1; }                  // the part of the list held in shared memory
+      }
+      S.cur[s][d] = 0; S.len[s][d] = (uint8_t)len; S.more[s][d] = (uint8_t)more;
     }
-    S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd; S.observed[s] = 0;
-    for (int w = 0; w < RTW; w++) S.pmask[s][w] = 0;
+    S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd; S.observed[s] = 0; S.pu[s] = -1;
     if (s < ns) {
-      S.reqs[s] = a.reqs[s];
-      const Req &r = a.reqs[s];
+      S.reqs[s] = a.rd->reqs[s];
+      const Req &r = a.rd->reqs[s];
       S.rq_single[s] = req_is_single(r); S.rq_core[s] = r.core[0]; S.rq_mem[s] = r.mem[0];
       S.rq_cmask[s] = r.C >= 4 ? 0xFFFFFFFFu : ((1u << (8 * r.C)) - 1u);   // alloc planes >= C are never written
-      for (int c = 0; c < r.C; c++) mono &= r.core[c] >= 0 && r.mem[c] >= 0;
     }
   }
-  mono = __all_sync(0xffffffffu, mono);
-  for (int s = 0; s < ns; s++)
-    for (int e = lane; e < DK; e += 32) S.lkey[s][e] = a.bufs[e / RK].cand[s][e % RK].key;
-  __syncwarp();
-  for (int i = lane; i < ns * D; i += 32) list_head_update(S, i / D, i % D);
-  __syncwarp();
-  for (int s = 0; s < ns; s++) prefetch_head(S, a, s, D, lane);
-  cp_async_commit();
-  int nT = 0, done = 0, reason = 0, n_observed = 0, flushed = 0;
-  for (int i = lane; i < 2048; i += 32) S.set_idx[i] = -1;
-  __syncwarp();
-  if (lane < ns && a.set.slot[lane] < 2048) S.set_idx[a.set.slot[lane]] = (int8_t)lane;
-  __syncwarp();
-  // pod -> shape index of the round, resolved 32 pods at a time (current block + the next one, so that a
-  // 4-pod window may straddle the block boundary); -1: shape not in the set / past the limit
-  auto load_block = [&](int blk) -> int {
-    const int q = a.p0 + blk * 32 + lane;
-    if (q >= a.p_limit) return -1;
-    const int slot = a.pod_slot[q];
-    return slot < 2048 ? (int)S.set_idx[slot] : -1;
-  };
-  int cur_blk = 0, myshape = load_block(0), nxshape = load_block(1);
-  // ---- sequential replay
-  int p = a.p0;
+  for (int e = tid; e < ns * D * rke; e += nthreads) {
+    const int k = e % rke, sd = e / rke, d = sd % D, s = sd / D;
+    const int len = reinterpret_cast<const int *>(a.bufs + (size_t)d * a.L.bytes + a.L.off_len)[s];
+    lk[e] = k < len ? *reinterpret_cast<const unsigned long long *>(a.bufs + (size_t)d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + k) * a.L.cand_bytes) : 0ull;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    bool mono = true;                                            // all requests >= 0: rows only decrease in this round
+    for (int s = 0; s < ns; s++) for (int c = 0; c < S.reqs[s].C; c++) mono &= S.reqs[s].core[c] >= 0 && S.reqs[s].mem[c] >= 0;
+    S.mono = mono ? 1 : 0;
+  }
+  for (int i = tid; i < ns * D; i += nthreads) list_head_update(S, lk, D, rke, i / D, i % D);
+  __syncthreads();
+  for (int s = tid; s < ns; s += nthreads) best_head_update(S, D, s);
+  __syncthreads();
+  const int p0 = S.p0, p_end = S.p_end;
 #ifdef EGS_RESOLVE_PROF
   long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64();
 #endif
-  while (p < a.p_limit) {
-    const int rel = p - a.p0;
-    if ((rel >> 5) != cur_blk) { cur_blk = rel >> 5; myshape = nxshape; nxshape = load_block(cur_blk + 1); }
-    while (rel - flushed >= 32) { __syncwarp(); flush_outputs(S, a.out, a.p0 + flushed, flushed, 32, lane); flushed += 32; }
-    const int ri = rel & 31;
-    // ======== fast path: up to 4 consecutive pods with distinct single-container shapes, decided by four
-    // 8-lane groups at once.  Preconditions make the decisions independent of each other's commits except
-    // for the hazards checked below; requires rows to be monotone and every shape of the round observed.
-    if (mono && n_observed == ns && nT + 4 <= RT) {
-      int sq[4]; int W = 0;
+  // ---- the owner loop.  Pods of shapes si with si % nw == warp, in pod order.
+  if (warp < nw) {
+    // own pods are found 128 at a time: lane loads 4 shape indices
+    int cb = p0 & ~3;                                            // chunk base (multiple of 4)
+    unsigned pm[4] = {0, 0, 0, 0};                               // per j: lanes whose pod 4*lane+j is mine
+    uint32_t myword = 0;
+    auto load_chunk = [&](int base) {
+      const int q = base + 4 * lane;
+      uint32_t wd = 0xFFFFFFFFu;
+      if (q < p_end) wd = *reinterpret_cast<const uint32_t *>(a.pod_sidx + q);   // padded allocation: reads up to 3 past the end
+      myword = wd;
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int i = ri + q;
-        const int v0 = __shfl_sync(0xffffffffu, myshape, i & 31), v1 = __shfl_sync(0xffffffffu, nxshape, i & 31);
-        sq[q] = i < 32 ? v0 : v1;
+      for (int j = 0; j < 4; j++) {
+        const int si = (wd >> (8 * j)) & 0xFF;
+        const bool mine = (q + j >= p0) && (q + j < p_end) && si < ns && (si % nw) == warp;
+        pm[j] = __ballot_sync(0xffffffffu, mine);
       }
-      {
-        bool okq = true;
+    };
+    load_chunk(cb);
+    const bool mono = S.mono != 0;
+    while (true) {
+      // next own pod
+      int p = -1, s = 0;
+      while (true) {
+        int best_i = 1 << 30;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          okq = okq && sq[q] >= 0;
-          for (int i = 0; i < q; i++) okq = okq && sq[q] != sq[i];
-          if (okq) W = q + 1;
+        for (int j = 0; j < 4; j++) if (pm[j]) { const int i = 4 * (__ffs(pm[j]) - 1) + j; best_i = min(best_i, i); }
+        if (best_i < (1 << 30)) {
+          const int j = best_i & 3, l = best_i >> 2;
+          pm[j] &= ~(1u << l);
+          p = cb + best_i;
+          s = (__shfl_sync(0xffffffffu, myword, l) >> (8 * j)) & 0xFF;
+          break;
         }
+        cb += 128;
+        if (cb >= p_end) break;
+        load_chunk(cb);
       }
-      const int sg = grp == 0 ? sq[0] : grp == 1 ? sq[1] : grp == 2 ? sq[2] : max(sq[3], 0);
-      const int sgs = max(sg, 0);                                  // safe index for inactive groups
-      // per group: single shape? at most one pending slot? list dry?   (all lanes execute; no group masks)
-      unsigned long long head = 0; int u;
-      {
-        const unsigned word = gl < ((nT + 31) >> 5) ? S.pmask[sgs][gl] : 0u;
-        const int cnt = seg8_add(__popc(word));
-        u = seg8_max(word ? gl * 32 + __ffs(word) - 1 : -1);
-        bool dry = false;
-        if (gl < D) { head = S.hkey[sgs][gl]; dry = head == 0 && S.more[sgs][gl] != 0; }
-        const bool bad = cnt > 1 || !S.rq_single[sgs] || dry;
-        const unsigned badm = __ballot_sync(0xffffffffu, bad);
-#pragma unroll
-        for (int q = 3; q >= 0; q--) if ((badm >> (8 * q)) & 0xFFu) W = min(W, q);
+      if (p < 0) break;
+      // ---- preparation outside the ticket (only owner-private data): best tracked option of s
+      const bool fast = mono && S.rq_single[s] && ld_vol(&S.n_observed) == ns;
+      unsigned long long pre_best = 0; int pre_t = -1, pre_nT = 0;
+      if (fast) {
+        pre_nT = ld_vol(&S.nT);
+        __threadfence_block();
+        unsigned long long b = 0; int bt = -1;
+        for (int t = lane; t < pre_nT; t += 32) { const unsigned long long k = S.tkey[s][t]; if (k > b) { b = k; bt = t; } }
+        int owner;
+        pre_best = warp_max_key(b, owner);
+        pre_t = __shfl_sync(0xffffffffu, bt, owner);
       }
       PROF_T(0)
-      if (W >= 2) {
-        // ---- decisions (read-only on shared state); groups >= W compute on a valid shape and are ignored
-        const int rq_c = S.rq_core[sgs], rq_m = S.rq_mem[sgs];
-        const int uu = max(u, 0);
-        // Trade of the one absent option, lane == GPU
-        const int c = S.rc[uu][gl], m = S.rm[uu][gl];
-        const int cmin = (int)seg8_minu((unsigned)c), mmin = (int)seg8_minu((unsigned)m);
-        const int c1 = seg8_max(c), m1 = seg8_max(m);
-        const int c2 = seg8_max(c == c1 ? INT32_MIN : c), m2 = seg8_max(m == m1 ? INT32_MIN : m);
-        const unsigned ceq = (__ballot_sync(0xffffffffu, c == c1) >> (8 * grp)) & 0xFFu;
-        const unsigned meq = (__ballot_sync(0xffffffffu, m == m1) >> (8 * grp)) & 0xFFu;
-        const int cex = (c == c1 && __popc(ceq) == 1) ? c2 : c1, mex = (m == m1 && __popc(meq) == 1) ? m2 : m1;
-        const bool okt = c >= rq_c && m >= rq_m;
-        const int nc = c - rq_c, nm = m - rq_m;
-        const int x = (max(mex, nm) + max(cex, nc)) - (min(mmin, nm) + min(cmin, nc));
-        const int key = (!okt || u < 0) ? -1 : (a.policy == EGS_BINPACK ? (x >> 2) * 8 + gl : gl);
-        const int bk = seg8_max(key);
-        const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
-        const uint32_t nd = (uint32_t)S.node[uu];
-        const unsigned long long tradekey = bk >= 0 ? cand_key(sc, nd) : 0ull;
-        unsigned long long best = 0; int best_t = -1;
-        for (int t = gl; t < nT; t += 8) {                         // the pending slot holds key 0 (zeroed by its bind)
-          const unsigned long long k = S.tkey[sgs][t];
-          if (k > best) { best = k; best_t = t; }
+      // ---- wait for the ticket
+      bool stopped = false;
+      while (true) {
+        const int t = ld_vol(&S.turn);
+        if (t == p) break;
+        if (ld_vol(&S.stop)) { stopped = true; break; }
+        if (p - t > 6) __nanosleep(200);
+      }
+      if (stopped) break;
+      __threadfence_block();
+      PROF_T(1)
+      int reason = 0;
+      const int pu = S.pu[s];
+      if (fast && pu != -2) {
+        // ================= fast pod: single-container shape, monotone round, every shape observed, <= 1 pending
+        const int nT = S.nT;
+        const int u = pu, uu = max(u, 0);
+        const int gl = lane & 7;
+        const int4 c0 = *reinterpret_cast<const int4 *>(&S.rc[uu][0]), c1 = *reinterpret_cast<const int4 *>(&S.rc[uu][4]);
+        const int4 m0 = *reinterpret_cast<const int4 *>(&S.rm[uu][0]), m1 = *reinterpret_cast<const int4 *>(&S.rm[uu][4]);
+        const uint32_t und = (uint32_t)S.node[uu];
+        const unsigned long long head = S.bh[s];
+        const int dry = S.dry[s];
+        const int rq_c = S.rq_core[s], rq_m = S.rq_mem[s];
+        unsigned long long best = pre_best; int best_t = pre_t;
+        if (nT > pre_nT) {                                        // slots installed by other shapes since the preparation
+          if (nT - pre_nT <= 4) {
+            for (int t = pre_nT; t < nT; t++) { const unsigned long long k = S.tkey[s][t]; if (k > best) { best = k; best_t = t; } }
+          } else {
+            unsigned long long b = 0; int bt = -1;
+            for (int t = pre_nT + lane; t < nT; t += 32) { const unsigned long long k = S.tkey[s][t]; if (k > b) { b = k; bt = t; } }
+            int owner;
+            const unsigned long long xb = warp_max_key(b, owner);
+            const int xt = __shfl_sync(0xffffffffu, bt, owner);
+            if (xb > best) { best = xb; best_t = xt; }
+          }
         }
+        int bk = -1;
+        if (u >= 0) {
+          const int c[EGS_G] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          const int m[EGS_G] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          bk = trade_lanes(c, m, gl, rq_c, rq_m, a.policy);
+        }
+        const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
+        const unsigned long long tradekey = bk >= 0 ? cand_key(sc, und) : 0ull;
         if (tradekey > best) { best = tradekey; best_t = u; }
         const bool from_head = head > best;
-        const unsigned long long mine = from_head ? head : best;
-        const unsigned long long win = seg8_max64(mine);
-        const unsigned wm = (__ballot_sync(0xffffffffu, mine == win && win != 0) >> (8 * grp)) & 0xFFu;
-        const int ownl = wm ? __ffs(wm) - 1 : 0;                     // lane inside the group
-        const int fh = __shfl_sync(0xffffffffu, (int)from_head, grp * 8 + ownl);
-        const int tw = __shfl_sync(0xffffffffu, best_t, grp * 8 + ownl);
-        // the shape's aggregates after this pod's filter (group-uniform)
-        const int fit = S.afit[sgs] + (bk >= 0);
-        const unsigned long long fd = S.afd[sgs] + (bk >= 0 ? S.fterm[uu] : 0ull);
-        const unsigned long long sd = S.asd[sgs] + (bk >= 0 ? score_term_b(S.sbase[uu], sc) : 0ull);
-        PROF_T(1)
-        // ---- hazards: a head-win changes lists / the tracked set for everyone after it; a pending node
-        // that an earlier pod of the group binds must be Traded on the rows AFTER that bind.
-        int hfh[4], ht[4], hu[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          hfh[q] = __shfl_sync(0xffffffffu, (int)(win != 0 && fh), 8 * q);
-          ht[q] = __shfl_sync(0xffffffffu, (win != 0 && !fh) ? tw : -2 - q, 8 * q);
-          hu[q] = __shfl_sync(0xffffffffu, u, 8 * q);
-        }
-        int Wc = W;
-#pragma unroll
-        for (int j = 3; j >= 1; j--) {
-          bool hz = false;
-#pragma unroll
-          for (int i = 0; i < j; i++) hz |= hfh[i] || (hu[j] >= 0 && hu[j] == ht[i]);
-          if (hz && j < Wc) Wc = j;
-        }
-        // pods that can commit side by side: tracked wins on pairwise distinct slots (and NOFIT pods);
-        // a head-win (always the last committed pod) goes through the sequential commit
-        int Ws = Wc;
-#pragma unroll
-        for (int j = 3; j >= 0; j--) {
-          bool dup = hfh[j];
-#pragma unroll
-          for (int i = 0; i < j; i++) dup |= ht[i] == ht[j];
-          if (dup && j < Ws) Ws = j;
-        }
-        PROF_T(2)
-        // ---- commits side by side: group leaders write disjoint rows (shape) and slots (node).
-        // Phase 1, every lane (safe indices for idle groups): read what the bind needs.
-        const bool act = grp < Ws;
-        const bool bindp = act && win != 0;
-        const int tb = bindp ? tw : 0;
-        const bool same = bindp && u == tb;                          // the node just Traded wins again (the common case)
-        const uint32_t masks = !bindp ? 1u : same ? (1u << (bk & 7)) : (S.al[sgs][tb] & 0xFFu);
-        const int gsel = __ffs(masks | 0x100u) - 1 & 7;
-        const int cc = S.rc[tb][gsel], mm = S.rm[tb][gsel];
-        const int okb = (cc >= rq_c && mm >= rq_m) ? 1 : 0;          // GPUs.Transact gpu.go:164-171
-        const int nodeb = S.node[tb];
-        const unsigned long long nfd = fd - S.fterm[tb], nsd = sd - score_term_b(S.sbase[tb], key_score(win));
-        __syncwarp();                                                // all reads done before any leader writes
-        // Phase 2, group leaders.
-        if (act && gl == 0) {
-          const unsigned ubit = 1u << (u & 31);
+        const unsigned long long win = from_head ? head : best;
+#ifdef EGS_RESOLVE_PROF
+        { const long long n_ = clock64(); prof[7] += n_ - tprev; }
+#endif
+        if (dry) reason = 3;
+        else if (win != 0 && from_head && nT >= NT) reason = 2;
+        if (reason == 0) {
+          // the shape's aggregates after this pod's filter
+          const int fit = S.afit[s] + (bk >= 0);
+          const unsigned long long fd = S.afd[s] + (bk >= 0 ? S.fterm[uu] : 0ull);
+          const unsigned long long sd = S.asd[s] + (bk >= 0 ? score_term_b(S.sbase[uu], sc) : 0ull);
           int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
-          if (u >= 0 && !same) {                                     // this pod's filter Traded slot u
-            if (bk >= 0) { S.st[sgs][u] = OPT_CACHED; S.al[sgs][u] = 1u << (bk & 7); S.tkey[sgs][u] = tradekey; }
-            else S.st[sgs][u] = OPT_UNFIT;
-            S.pmask[sgs][u >> 5] &= ~ubit;
+          int tw = -1;
+          if (win != 0) {
+            tw = best_t;
+            uint32_t masks;
+            if (from_head) {
+              tw = nT;
+              const uint32_t w = key_node(win);
+              const int d = S.bh_d[s];
+              const char *cd = a.bufs + (size_t)d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + S.cur[s][d]) * a.L.cand_bytes;
+#ifdef EGS_RESOLVE_PROF
+              const long long i0_ = clock64();
+#endif
+              install_slot(S, a, cd, tw, w, ns, lane);
+              __syncwarp();
+#ifdef EGS_RESOLVE_PROF
+              const long long i1_ = clock64();
+#endif
+              heads_drop_node(S, lk, D, rke, ns, w, lane);
+              __syncwarp();
+#ifdef EGS_RESOLVE_PROF
+              { const long long i2_ = clock64(); prof[12] += i1_ - i0_; prof[13] += i2_ - i1_; }
+#endif
+              masks = S.al[s][tw] & 0xFFu;
+              PROF_C(11, 1)
+            } else {
+              masks = (tw == u) ? (1u << (bk & 7)) : (S.al[s][tw] & 0xFFu);
+            }
+            const int g = __ffs(masks) - 1;
+            const int cc = S.rc[tw][g], mm = S.rm[tw][g];
+            const int ok = (cc >= rq_c && mm >= rq_m) ? 1 : 0;    // GPUs.Transact gpu.go:164-171
+            o_node = S.node[tw];
+            __syncwarp();
+            if (lane == 0) {
+              if (ok) { S.rc[tw][g] = cc - rq_c; S.rm[tw][g] = mm - rq_m; }
+              S.dirty[tw] = 1;
+              if (from_head) { __threadfence_block(); S.nT = nT + 1; }
+            }
+            o_status = ok ? EGS_OK : EGS_ERR_TRANSACT; o_masks = ok ? masks : 0;
           }
-          if (bindp) {
-            S.st[sgs][tb] = OPT_ABSENT; S.tkey[sgs][tb] = 0; S.pmask[sgs][tb >> 5] |= 1u << (tb & 31);   // node.go:90-92
-            S.afit[sgs] = fit - 1; S.afd[sgs] = nfd; S.asd[sgs] = nsd; S.dirty[tb] = 1;
-            if (okb) { S.rc[tb][gsel] = cc - rq_c; S.rm[tb][gsel] = mm - rq_m; }
-            o_node = nodeb; o_status = okb ? EGS_OK : EGS_ERR_TRANSACT; o_masks = okb ? masks : 0;
-          } else if (u >= 0 && bk >= 0) {                            // nothing fits elsewhere, but the Trade result stands
-            S.afit[sgs] = fit; S.afd[sgs] = fd; S.asd[sgs] = sd;
-          }
-          const int r = (rel + grp) & 63;
-          S.o_node[r] = o_node; S.o_status[r] = o_status; S.o_fit[r] = fit; S.o_fd[r] = fd; S.o_sd[r] = sd; S.o_alloc[r] = o_masks;
-        }
-        __syncwarp();
-        // ---- the rest (a head-win, or pods sharing a node) in pod order
-        if (Ws < Wc) {
-          if (gl == 0 && grp >= Ws && grp < Wc) {
-            PodRec r;
-            r.s = sg; r.u = u; r.bk = bk; r.from_head = fh; r.t = tw; r.d = ownl; r.pad = sc;
-            r.fit = fit; r.fd = fd; r.sd = sd; r.win = win;
-            recs[grp] = r;
+          // ---- release the ticket, then the owner-private part
+          __syncwarp();
+          if (lane == 0) { __threadfence_block(); st_vol(&S.turn, p + 1); }
+#ifdef EGS_RESOLVE_PROF
+          { const long long n_ = clock64(); prof[from_head && win != 0 ? 5 : 2] += n_ - tprev; tprev = n_; }
+#endif
+          PROF_C(6, 1)
+          if (lane == 0) {
+            const unsigned ubit = 1u << (u & 31);
+            if (u >= 0 && u != tw) {                              // this pod's filter Traded slot u
+              if (bk >= 0) { S.st[s][u] = OPT_CACHED; S.al[s][u] = 1u << (bk & 7); S.tkey[s][u] = tradekey; }
+              else S.st[s][u] = OPT_UNFIT;
+              S.pmask[s][u >> 5] &= ~ubit;
+            }
+            if (tw >= 0) {                                        // node.go:90-92: the entry is consumed
+              S.st[s][tw] = OPT_ABSENT; S.tkey[s][tw] = 0; S.pmask[s][tw >> 5] |= 1u << (tw & 31);
+              S.afit[s] = fit - 1; S.afd[s] = fd - S.fterm[tw]; S.asd[s] = sd - score_term_b(S.sbase[tw], key_score(win));
+              S.pu[s] = tw;
+            } else {
+              S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd;
+              S.pu[s] = -1;
+            }
+            if (a.out.node) a.out.node[p] = o_node;
+            if (a.out.status) a.out.status[p] = o_status;
+            if (a.out.fit_count) a.out.fit_count[p] = fit;
+            if (a.out.fit_digest) a.out.fit_digest[p] = fd;
+            if (a.out.score_digest) a.out.score_digest[p] = sd;
+            if (a.out.alloc) reinterpret_cast<uint32_t *>(a.out.alloc)[p] = o_masks;
           }
           __syncwarp();
-          for (int q = Ws; q < Wc; q++) {
-            const PodRec r = recs[q];
-            if (r.u >= 0 && lane == 0) {                             // this pod's filter Traded slot u
-              if (r.bk >= 0) { S.st[r.s][r.u] = OPT_CACHED; S.al[r.s][r.u] = 1u << (r.bk & 7); S.tkey[r.s][r.u] = cand_key(r.pad, (uint32_t)S.node[r.u]); }
-              else S.st[r.s][r.u] = OPT_UNFIT;
-              S.pmask[r.s][r.u >> 5] &= ~(1u << (r.u & 31));
-            }
-            __syncwarp();
-            commit_pod(S, a, lane, rel + q, r.s, r.win, r.from_head, r.t, r.d, r.fit, r.fd, r.sd, mono, ns, D, nT, n_observed, PROF_PTR);
-          }
+          PROF_T(3)
+          continue;
         }
-        PROF_T(3) PROF_C(6, 1) PROF_C(7, Wc) PROF_C(8, W)
-        p += Wc; done += Wc;
-        continue;
+      } else {
+        reason = general_pod(S, a, lk, lane, p, s, ns, D, rke);
+        PROF_C(9, 1)
       }
-    }
-    // ======== general path: one pod
-    const int s = __shfl_sync(0xffffffffu, myshape, ri);
-    if (s < 0) { reason = 1; break; }                            // shape outside this round's set
-    if (nT >= RT) { reason = 2; break; }                          // no free tracked slot for a new winner
-    // best untracked candidate per shard (cached heads; consumed entries were skipped when they were zeroed)
-    unsigned long long head = 0; bool dry = false;
-    if (lane < D) { head = S.hkey[s][lane]; dry = head == 0 && S.more[s][lane] != 0; }
-    if (__ballot_sync(0xffffffffu, dry)) { reason = 3; break; }   // a truncated list ran dry: next round
-    if (!S.observed[s]) {                                          // first pod of this shape in the round:
-      for (int t = lane; t < nT; t += 32) if (S.st[s][t] == OPT_NEW) S.st[s][t] = OPT_CACHED;   // NEW options are now ordinary
-      __syncwarp();
-      if (lane == 0) S.observed[s] = 1;
-      n_observed++;
-      __syncwarp();
-    }
-    const int single = S.rq_single[s];
-    // tracked nodes: Trade absent options NOW (this pod's filter); best tracked option
-    unsigned long long best = 0; int best_t = -1;
-    const int nw = (nT + 31) >> 5;
-    for (int w = 0; w < nw; w++) {
-      unsigned word = S.pmask[s][w];
-      if (word) {
-        if (single) {
-          // 8 lanes per pending node (lane == GPU), up to 4 nodes at a time
-          const int rq_c = S.rq_core[s], rq_m = S.rq_mem[s];
-          while (word) {
-            int bsel = -1;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const int b = word ? __ffs(word) - 1 : -1;
-              if (word) word &= word - 1;
-              if (q == grp) bsel = b;
-            }
-            bool okl = false; int sc = 0; int t = 0;
-            if (bsel >= 0) {                                       // group-uniform
-              t = w * 32 + bsel;
-              const int c = S.rc[t][gl], m = S.rm[t][gl];
-              const int cmin = (int)__reduce_min_sync(gmask, (unsigned)c), mmin = (int)__reduce_min_sync(gmask, (unsigned)m);
-              const int c1 = __reduce_max_sync(gmask, c), m1 = __reduce_max_sync(gmask, m);
-              const int c2 = __reduce_max_sync(gmask, c == c1 ? INT32_MIN : c), m2 = __reduce_max_sync(gmask, m == m1 ? INT32_MIN : m);
-              const bool cu = __popc(__ballot_sync(gmask, c == c1)) == 1, mu = __popc(__ballot_sync(gmask, m == m1)) == 1;
-              const int cex = (c == c1 && cu) ? c2 : c1, mex = (m == m1 && mu) ? m2 : m1;   // max over the OTHER GPUs
-              const bool ok = c >= rq_c && m >= rq_m;                                         // gpu.go:55
-              const int nc = c - rq_c, nm = m - rq_m;
-              const int x = (max(mex, nm) + max(cex, nc)) - (min(mmin, nm) + min(cmin, nc));
-              const int key = !ok ? -1 : (a.policy == EGS_BINPACK ? (x >> 2) * 8 + gl : gl);
-              const int bk = __reduce_max_sync(gmask, key);
-              if (gl == 0) {
-                if (bk >= 0) {
-                  sc = a.policy == EGS_BINPACK ? (bk >> 3) * 100 : 0;
-                  S.st[s][t] = OPT_CACHED; S.al[s][t] = 1u << (bk & 7); S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]);
-                  okl = true;
-                } else {
-                  S.st[s][t] = OPT_UNFIT;
-                }
-              }
-            }
-            for (unsigned rem = __ballot_sync(0xffffffffu, okl); rem; rem &= rem - 1) {   // usually one leader
-              if (lane == __ffs(rem) - 1) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term_b(S.sbase[t], sc); }
-              __syncwarp();
-            }
-          }
-        } else {
-          const int t = w * 32 + lane;
-          bool ok = false; int sc = 0;
-          if ((word >> lane) & 1u) {
-            uint32_t masks;
-            ok = trade_general(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], a.policy, sc, masks);
-            if (ok) { S.st[s][t] = OPT_CACHED; S.al[s][t] = masks; S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]); }
-            else S.st[s][t] = OPT_UNFIT;
-          }
-          for (unsigned rem = word; rem; rem &= rem - 1) {
-            if (lane == __ffs(rem) - 1 && ok) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term_b(S.sbase[t], sc); }
-            __syncwarp();
-          }
-        }
-        __syncwarp();
-        if (lane == 0) S.pmask[s][w] = 0;
+      if (reason) {                                               // the round ends BEFORE pod p
+        if (lane == 0) { S.stop_reason = reason; __threadfence_block(); st_vol(&S.stop, 1); }
+        break;
       }
-      const int t = w * 32 + lane;
-      const unsigned long long k = t < nT ? S.tkey[s][t] : 0ull;
-      if (k > best) { best = k; best_t = t; }
+      __syncwarp();
+      if (lane == 0) { __threadfence_block(); st_vol(&S.turn, p + 1); }
+      PROF_T(4)
     }
-    __syncwarp();
-    // winner = max over (tracked options, untracked list heads): two redux.sync steps on the key halves
-    const bool from_head = head > best;
-    const unsigned long long mine = from_head ? head : best;
-    const unsigned hi = (unsigned)(mine >> 32);
-    const unsigned m1 = __reduce_max_sync(0xffffffffu, hi);
-    const unsigned m2 = __reduce_max_sync(0xffffffffu, hi == m1 ? (unsigned)mine : 0u);
-    const unsigned long long win = ((unsigned long long)m1 << 32) | m2;
-    int owner = 0, fh = 0, tw = -1;
-    if (win != 0) {
-      owner = __ffs(__ballot_sync(0xffffffffu, mine == win)) - 1;
-      fh = __shfl_sync(0xffffffffu, (int)from_head, owner);
-      tw = __shfl_sync(0xffffffffu, best_t, owner);
-    }
-    PROF_T(4)
-    commit_pod(S, a, lane, rel, s, win, fh, tw, owner, S.afit[s], S.afd[s], S.asd[s], mono, ns, D, nT, n_observed, PROF_PTR);
-    PROF_T(5) PROF_C(9, 1)
-    p++; done++;
   }
-  __syncwarp();
-  while (done > flushed) { const int n = min(32, done - flushed); flush_outputs(S, a.out, a.p0 + flushed, flushed, n, lane); flushed += n; }
+  __syncthreads();
   // ---- epilogue: write the tracked nodes back (each shard its own nodes)
-  for (int t = 0; t < nT; t++) {
+  const int nT = S.nT;
+  const int done = (S.stop ? S.turn : p_end) - p0;
+  const int nwarps = nthreads >> 5;
+  for (int t = warp; t < nT; t += nwarps) {
     const int w = S.node[t];
     if (w < a.lo || w >= a.hi) continue;
     if (S.dirty[t]) {
       if (lane < EGS_G) a.core[(size_t)w * EGS_G + lane] = S.rc[t][lane];
       else if (lane < 2 * EGS_G) a.mem[(size_t)w * EGS_G + lane - EGS_G] = S.rm[t][lane - EGS_G];
     }
-    if (lane < ns) {
-      const int slot = a.set.slot[lane];
-      const uint8_t st = S.st[lane][t];
+    for (int s = lane; s < ns; s += 32) {
+      const int slot = a.rd->slot[s];
+      const uint8_t st = S.st[s][t];
       tb_st(a.tb, slot)[w] = st;
       if (st == OPT_CACHED || st == OPT_NEW) {
-        tb_sc(a.tb, slot)[w] = key_score(S.tkey[lane][t]);
+        tb_sc(a.tb, slot)[w] = key_score(S.tkey[s][t]);
         uint8_t *alp = tb_al(a.tb, slot);
-        const uint32_t am = S.al[lane][t];
-        for (int c = 0; c < S.reqs[lane].C; c++) alp[(size_t)c * a.tb.n_pad + w] = (uint8_t)(am >> (8 * c));
+        const uint32_t am = S.al[s][t];
+        for (int c = 0; c < S.reqs[s].C; c++) alp[(size_t)c * a.tb.n_pad + w] = (uint8_t)(am >> (8 * c));
       }
     }
     if (S.dirty[t]) {                                            // shapes outside the round set
       for (int slot = lane; slot < a.tb.n_slots; slot += 32) {
         bool in_set = false;
-        for (int q = 0; q < ns; q++) in_set |= a.set.slot[q] == slot;
+        for (int q = 0; q < ns; q++) in_set |= a.rd->slot[q] == slot;
         if (in_set) continue;
         uint8_t *q = tb_st(a.tb, slot) + w;
         if (*q == OPT_UNFIT) *q = OPT_ABSENT;
@@ -855,10 +973,16 @@ __global__ void __launch_bounds__(32) k_resolve(ResolveArgs a) {
       }
     }
   }
-  if (lane < ns && S.observed[lane]) a.obs_pending[a.set.slot[lane]] = 1;
-  if (lane == 0) { a.done[0] = done; a.done[1] = nT; a.done[2] = reason; }
+  for (int s = tid; s < ns; s += nthreads) if (S.observed[s]) a.obs_pending[a.rd->slot[s]] = 1;
+  if (tid == 0) {
+    RoundCtl *c = a.ctl;
+    c->next_p = p0 + done;
+    if (done < 1) c->error = 1;                                  // no progress: the host reports it
+    c->rounds += 1; c->pods += done; c->tracked += nT;
+    c->stops[S.stop ? (S.stop_reason & 3) : 0] += 1;
+  }
 #ifdef EGS_RESOLVE_PROF
-  if (lane == 0) for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)a.prof + i, (unsigned long long)prof[i]);
+  if (lane == 0 && warp < nw) for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)&a.ctl->prof[i], (unsigned long long)prof[i]);
 #endif
 }
 
@@ -881,18 +1005,20 @@ struct egs_handle;
 
 struct RoundsState {
   void *comm = nullptr;             // ncclComm_t
-  int32_t *d_pod_slot = nullptr; int pod_cap = 0;
+  uint8_t *d_pod_sidx = nullptr; int pod_cap = 0;
   uint8_t *d_obs = nullptr; int obs_cap = 0;
-  unsigned long long *d_cta_lists = nullptr; AggPart *d_cta_agg = nullptr; int grid = 0;
-  ShardBuf *d_bufs = nullptr;       // [RD]; own shard written at index `rank`
-  int32_t *d_done = nullptr; int32_t *h_done = nullptr; long long *d_prof = nullptr;
+  unsigned long long *d_cta_lists = nullptr; AggPart *d_cta_agg = nullptr; int grid = 0, cta_nsc = 0;
+  char *d_bufs = nullptr; size_t bufs_cap = 0;      // [RD] candidate buffers; own shard written at index `rank`
+  RoundDesc *d_rd = nullptr; RoundDesc *h_rd = nullptr;
+  RoundCtl *d_ctl = nullptr; RoundCtl *h_ctl = nullptr;
   int64_t rounds = 0, pods = 0, tracked = 0; int64_t stops[4] = {0, 0, 0, 0};
+  long long prof[16] = {0};
 };
 
 static int batch_rescan(egs_handle *h, int P, const int32_t *c_off, const egs_unit *units,
                         const std::vector<int> &slots, PodOut out);
 static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_unit *units,
-                        const std::vector<int> &slots, PodOut out);
+                        const std::vector<int> &slots, PodOut out, int *n_done);
 static void rounds_free(RoundsState *r);
 static int rounds_comm_unique_id(uint8_t out_id[128]);
 static int rounds_comm_init(egs_handle *h, const uint8_t id[128]);

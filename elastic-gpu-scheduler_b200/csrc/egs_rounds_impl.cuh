@@ -42,9 +42,10 @@ static NcclApi *nccl_api() {
 
 static void rounds_free(RoundsState *r) {
   if (r->comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)r->comm);
-  void *dev[] = {r->d_pod_slot, r->d_obs, r->d_cta_lists, r->d_cta_agg, r->d_bufs, r->d_done, r->d_prof};
+  void *dev[] = {r->d_pod_sidx, r->d_obs, r->d_cta_lists, r->d_cta_agg, r->d_bufs, r->d_rd, r->d_ctl};
   for (void *p : dev) if (p) cudaFree(p);
-  if (r->h_done) cudaFreeHost(r->h_done);
+  if (r->h_rd) cudaFreeHost(r->h_rd);
+  if (r->h_ctl) cudaFreeHost(r->h_ctl);
   *r = RoundsState();
 }
 
@@ -67,30 +68,51 @@ static int rounds_comm_init(egs_handle *h, const uint8_t id[128]) {
   return EGS_OK;
 }
 
-static int rounds_ensure(egs_handle *h, int P) {
+
+// ---- resolver configuration by the size of the round's shape set
+struct MwConfig { int inst; int nt; int rkm; size_t smem_struct; };
+static MwConfig mw_config(int ns) {
+  MwConfig c;
+  if (ns <= 16) { c.inst = 0; c.nt = 512; c.rkm = 128; c.smem_struct = sizeof(MwSmem<16, 512>); }
+  else if (ns <= 32) { c.inst = 1; c.nt = 256; c.rkm = 64; c.smem_struct = sizeof(MwSmem<32, 256>); }
+  else { c.inst = 2; c.nt = 128; c.rkm = 32; c.smem_struct = sizeof(MwSmem<RSMAX, 128>); }
+  c.smem_struct = (c.smem_struct + 15) & ~(size_t)15;
+  return c;
+}
+#define MW_SMEM_MAX 232448   // 227 KB opt-in limit per CTA on sm_100
+
+static int rounds_ensure(egs_handle *h, int P, const BufLayout &L) {
   RoundsState &R = h->rounds;
-  if (!R.d_bufs) {
-    CK(h, cudaMalloc(&R.d_bufs, sizeof(ShardBuf) * RD));
-    CK(h, cudaMemsetAsync(R.d_bufs, 0, sizeof(ShardBuf) * RD, h->stream));
-    CK(h, cudaMalloc(&R.d_done, sizeof(int32_t) * 4));
-    CK(h, cudaMalloc(&R.d_prof, sizeof(long long) * 16));
-    CK(h, cudaMemsetAsync(R.d_prof, 0, sizeof(long long) * 16, h->stream));
-    CK(h, cudaMallocHost(&R.h_done, sizeof(int32_t) * 4));
-    CK(h, cudaFuncSetAttribute(k_resolve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ResolveSmem)));
+  if (!R.d_ctl) {
+    CK(h, cudaMalloc(&R.d_ctl, sizeof(RoundCtl)));
+    CK(h, cudaMallocHost(&R.h_ctl, sizeof(RoundCtl)));
+    CK(h, cudaMalloc(&R.d_rd, sizeof(RoundDesc)));
+    CK(h, cudaMallocHost(&R.h_rd, sizeof(RoundDesc)));
+    CK(h, cudaFuncSetAttribute(k_resolve_mw<16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
+    CK(h, cudaFuncSetAttribute(k_resolve_mw<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
+    CK(h, cudaFuncSetAttribute(k_resolve_mw<RSMAX, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
+  }
+  const size_t need = (size_t)L.bytes * RD;
+  if (need > R.bufs_cap) {
+    if (R.d_bufs) { CK(h, cudaStreamSynchronize(h->stream)); cudaFree(R.d_bufs); R.d_bufs = nullptr; R.bufs_cap = 0; }
+    CK(h, cudaMalloc(&R.d_bufs, need));
+    CK(h, cudaMemsetAsync(R.d_bufs, 0, need, h->stream));
+    R.bufs_cap = need;
   }
   const int chunks = (h->hi - h->lo + 127) / 128;
   const int grid = std::max(1, std::min((chunks + SEL_WARPS - 1) / SEL_WARPS, 296));
-  if (grid > R.grid) {
-    if (R.d_cta_lists) { cudaFree(R.d_cta_lists); cudaFree(R.d_cta_agg); }
-    CK(h, cudaMalloc(&R.d_cta_lists, sizeof(unsigned long long) * (size_t)grid * RS * RK));
-    CK(h, cudaMalloc(&R.d_cta_agg, sizeof(AggPart) * (size_t)grid * RS));
-    R.grid = grid;
+  if (grid > R.grid || L.nsc > R.cta_nsc) {
+    if (R.d_cta_lists) { CK(h, cudaStreamSynchronize(h->stream)); cudaFree(R.d_cta_lists); cudaFree(R.d_cta_agg); R.d_cta_lists = nullptr; }
+    const int g = std::max(grid, R.grid), n = std::max(L.nsc, R.cta_nsc);
+    CK(h, cudaMalloc(&R.d_cta_lists, sizeof(unsigned long long) * (size_t)g * n * RK));
+    CK(h, cudaMalloc(&R.d_cta_agg, sizeof(AggPart) * (size_t)g * n));
+    R.grid = g; R.cta_nsc = n;
   }
-  if (P > R.pod_cap) {
-    if (R.d_pod_slot) cudaFree(R.d_pod_slot);
+  if (P + 8 > R.pod_cap) {
+    if (R.d_pod_sidx) { CK(h, cudaStreamSynchronize(h->stream)); cudaFree(R.d_pod_sidx); }
     R.pod_cap = 0;
-    CK(h, cudaMalloc(&R.d_pod_slot, sizeof(int32_t) * (size_t)P));
-    R.pod_cap = P;
+    CK(h, cudaMalloc(&R.d_pod_sidx, (size_t)P + 8));
+    R.pod_cap = P + 8;
   }
   const int ns = (int)h->shapes.size();
   if (ns > R.obs_cap) {
@@ -108,34 +130,34 @@ static int rounds_ensure(egs_handle *h, int P) {
   return EGS_OK;
 }
 
+// Runs the batch; *n_done = pods resolved (== P unless an error stopped the loop).
 static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_unit *units,
-                        const std::vector<int> &slots, PodOut out) {
+                        const std::vector<int> &slots, PodOut out, int *n_done) {
   (void)c_off; (void)units;
   RoundsState &R = h->rounds;
+  *n_done = 0;
   if (h->world > 1 && !R.comm) return fail(h, EGS_ERR_COMM, "sharded handle without egs_comm_init");
   if (h->world > RD) return fail(h, EGS_ERR_BAD_ARG, "too many shards");
-  TRY(rounds_ensure(h, P));
-  // pod -> slot ids to the device (pinned staging)
-  TRY(ensure_stage(h, sizeof(int32_t) * (size_t)P));
-  CK(h, cudaStreamSynchronize(h->stream));
-  memcpy(h->h_stage, slots.data(), sizeof(int32_t) * (size_t)P);
-  CK(h, cudaMemcpyAsync(R.d_pod_slot, h->h_stage, sizeof(int32_t) * (size_t)P, cudaMemcpyHostToDevice, h->stream));
+
+  // distinct shapes of the whole batch, in order of first appearance: when they fit one round set the set
+  // is the same for every round, the round loop runs without the host (no per-round synchronisation)
+  std::vector<int> batch_shapes;
+  {
+    std::vector<char> seen(h->shapes.size(), 0);
+    for (int p = 0; p < P && (int)batch_shapes.size() <= RSMAX; p++)
+      if (!seen[slots[p]]) { seen[slots[p]] = 1; batch_shapes.push_back(slots[p]); }
+  }
+  const bool one_set = (int)batch_shapes.size() <= RSMAX;
+  const int ns_cfg = one_set ? (int)batch_shapes.size() : RSMAX;
+  const MwConfig cfg = mw_config(ns_cfg);
+  const BufLayout L = make_layout(ns_cfg, cfg.rkm);
+  TRY(rounds_ensure(h, P, L));
 
   TableSet tb; tb.st = h->d_st; tb.sc = h->d_sc; tb.al = h->d_al; tb.n_pad = (size_t)h->n_pad; tb.n_slots = (int)h->shapes.size();
   const int chunks = (h->hi - h->lo + 127) / 128;
   const int grid = std::max(1, std::min((chunks + SEL_WARPS - 1) / SEL_WARPS, 296));
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   if (h->timing) for (auto &e : ev) CK(h, cudaEventCreate(&e));
-
-  // distinct shapes of the whole batch, in order of first appearance: when they fit one round set the set
-  // is the same for every round and no per-round scan of the pod list is needed
-  std::vector<int> batch_shapes;
-  {
-    std::vector<char> seen(h->shapes.size(), 0);
-    for (int p = 0; p < P && (int)batch_shapes.size() <= RS; p++)
-      if (!seen[slots[p]]) { seen[slots[p]] = 1; batch_shapes.push_back(slots[p]); }
-  }
-  const bool one_set = (int)batch_shapes.size() <= RS;
 
   // Cold shapes (option table still all-absent, e.g. a fresh or restored scheduler): ONE full-evaluate launch
   // per shape over this shard's nodes fills the table (OPT_NEW / OPT_UNFIT) -- the HBM-roofline kernel,
@@ -144,7 +166,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     int cold = 0;
     for (int slot : batch_shapes) {
-      if ((int)batch_shapes.size() > RS && cold >= RS) break;
+      if (!one_set && cold >= RSMAX) break;
       if (!h->slot_cold[slot]) continue;
       if (!e0) { CK(h, cudaEventCreate(&e0)); CK(h, cudaEventCreate(&e1)); CK(h, cudaEventRecord(e0, h->stream)); }
       const Shape &sh = h->shapes[slot];
@@ -169,65 +191,143 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   for (int slot : batch_shapes) h->slot_cold[slot] = 0;
   for (int p = 0; p < P; p++) h->slot_cold[slots[p]] = 0;
 
-  int p0 = 0;
-  while (p0 < P) {
-    // the round's shape set: distinct shapes in pod order until RS are collected
-    SelectArgs sa; MergeArgs ma; ResolveArgs ra;
-    RoundSet set; set.n = 0;
-    int plim = p0;
-    const int pcap = std::min(P, p0 + 16384);    // a round never gets further (tracked table, list depth)
-    if (one_set) {
-      for (int q : batch_shapes) set.slot[set.n++] = q;
-      plim = pcap;
-    }
-    for (; plim < pcap; plim++) {
-      const int slot = slots[plim];
-      bool found = false;
-      for (int q = 0; q < set.n; q++) if (set.slot[q] == slot) { found = true; break; }
-      if (found) continue;
-      if (set.n == RS) break;
-      set.slot[set.n++] = slot;
-    }
-    for (int q = set.n; q < RS; q++) set.slot[q] = -1;
-    sa.core = h->d_core; sa.mem = h->d_mem; sa.mem_total = h->d_mem_total;
-    sa.lo = h->lo; sa.hi = h->hi; sa.policy = h->policy; sa.set = set; sa.tb = tb; sa.obs_pending = R.d_obs;
-    sa.cta_lists = R.d_cta_lists; sa.cta_agg = R.d_cta_agg;
-    memset(sa.reqs, 0, sizeof sa.reqs);
-    for (int q = 0; q < set.n; q++) sa.reqs[q] = make_req(h->shapes[set.slot[q]].C, h->shapes[set.slot[q]].u);
-    ma.core = h->d_core; ma.mem = h->d_mem; ma.mem_total = h->d_mem_total; ma.set = set; ma.tb = tb;
-    ma.obs_pending = R.d_obs; ma.cta_lists = R.d_cta_lists; ma.cta_agg = R.d_cta_agg; ma.n_cta = grid;
-    ma.out = R.d_bufs + h->rank;
-    ra.core = h->d_core; ra.mem = h->d_mem; ra.lo = h->lo; ra.hi = h->hi; ra.policy = h->policy; ra.n_shards = h->world;
-    ra.set = set; memcpy(ra.reqs, sa.reqs, sizeof ra.reqs); ra.tb = tb; ra.obs_pending = R.d_obs; ra.bufs = R.d_bufs;
-    ra.pod_slot = R.d_pod_slot; ra.p0 = p0; ra.p_limit = plim; ra.out = out; ra.done = R.d_done; ra.prof = R.d_prof;
+  // ---- resolver geometry
+  const int D = h->world;
+  int rke = cfg.rkm;
+  {
+    const size_t avail = MW_SMEM_MAX - cfg.smem_struct;
+    const size_t per = (size_t)ns_cfg * D * 8;
+    if ((size_t)rke * per > avail) rke = (int)(avail / per);
+    if (rke < 4) return fail(h, EGS_ERR_BAD_ARG, "rounds: shape set too large for the resolver's shared memory");
+  }
+  const int nw = std::max(1, std::min(ns_cfg, MW_MAX_WARPS));
+  const size_t smem = cfg.smem_struct + (size_t)ns_cfg * D * rke * 8;
 
+  SelectArgs sa; MergeArgs ma; MwArgs ra;
+  sa.core = h->d_core; sa.mem = h->d_mem; sa.mem_total = h->d_mem_total;
+  sa.lo = h->lo; sa.hi = h->hi; sa.policy = h->policy; sa.nsc = L.nsc; sa.rd = R.d_rd; sa.tb = tb; sa.obs_pending = R.d_obs;
+  sa.cta_lists = R.d_cta_lists; sa.cta_agg = R.d_cta_agg; sa.ctl = R.d_ctl;
+  ma.core = h->d_core; ma.mem = h->d_mem; ma.mem_total = h->d_mem_total; ma.rd = R.d_rd; ma.tb = tb;
+  ma.obs_pending = R.d_obs; ma.cta_lists = R.d_cta_lists; ma.cta_agg = R.d_cta_agg; ma.n_cta = grid;
+  ma.out = R.d_bufs + (size_t)h->rank * L.bytes; ma.L = L; ma.ctl = R.d_ctl;
+  ra.core = h->d_core; ra.mem = h->d_mem; ra.lo = h->lo; ra.hi = h->hi; ra.policy = h->policy; ra.n_shards = D;
+  ra.rd = R.d_rd; ra.tb = tb; ra.obs_pending = R.d_obs; ra.bufs = R.d_bufs; ra.L = L; ra.pod_sidx = R.d_pod_sidx;
+  ra.p0 = -1; ra.p_limit = 0; ra.out = out; ra.ctl = R.d_ctl; ra.rke = rke; ra.nw = nw;
+
+  int ns_round = ns_cfg;                                        // grid of k_merge
+  auto launch_round = [&]() -> int {
     if (h->timing) CK(h, cudaEventRecord(ev[0], h->stream));
     k_select<<<grid, SEL_THREADS, 0, h->stream>>>(sa);
     if (h->timing) CK(h, cudaEventRecord(ev[1], h->stream));
-    k_merge<<<set.n, 256, 0, h->stream>>>(ma);
+    k_merge<<<ns_round, 256, 0, h->stream>>>(ma);
     if (h->world > 1)
-      NCK(h, nccl_api()->AllGather(R.d_bufs + h->rank, R.d_bufs, sizeof(ShardBuf), ncclChar, (ncclComm_t)R.comm, h->stream));
+      NCK(h, nccl_api()->AllGather(R.d_bufs + (size_t)h->rank * L.bytes, R.d_bufs, (size_t)L.bytes, ncclChar, (ncclComm_t)R.comm, h->stream));
     if (h->timing) CK(h, cudaEventRecord(ev[2], h->stream));
-    k_resolve<<<1, 32, sizeof(ResolveSmem), h->stream>>>(ra);
+    if (cfg.inst == 0) k_resolve_mw<16, 512><<<1, 32 * nw, smem, h->stream>>>(ra);
+    else if (cfg.inst == 1) k_resolve_mw<32, 256><<<1, 32 * nw, smem, h->stream>>>(ra);
+    else k_resolve_mw<RSMAX, 128><<<1, 32 * nw, smem, h->stream>>>(ra);
     if (h->timing) CK(h, cudaEventRecord(ev[3], h->stream));
-    CK(h, cudaMemcpyAsync(R.h_done, R.d_done, sizeof(int32_t) * 4, cudaMemcpyDeviceToHost, h->stream));
+    h->k_launches[EGS_K_SELECT] += 1; h->k_launches[EGS_K_MERGE] += 1; h->k_launches[EGS_K_RESOLVE] += 1;
+    return EGS_OK;
+  };
+  auto read_ctl = [&]() -> int {
+    CK(h, cudaMemcpyAsync(R.h_ctl, R.d_ctl, sizeof(RoundCtl), cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaStreamSynchronize(h->stream));
     CK(h, cudaGetLastError());
-    const int done = R.h_done[0];
-    if (done < 1 || done > plim - p0) return fail(h, EGS_ERR_CUDA, "rounds: resolver made no progress");
-    p0 += done;
-    R.rounds++; R.pods += done; R.tracked += R.h_done[1]; R.stops[R.h_done[2] & 3]++;
-    h->k_launches[EGS_K_SELECT] += 2; h->k_launches[EGS_K_RESOLVE] += 1;
     if (h->timing) {
       float a = 0, b = 0, c = 0;
       cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
       h->k_ms[EGS_K_SELECT] += a; h->k_ms[EGS_K_MERGE] += b; h->k_ms[EGS_K_RESOLVE] += c;
     }
+    return EGS_OK;
+  };
+
+  // staging: pod -> shape index, round descriptor, control block
+  TRY(ensure_stage(h, (size_t)P + 8));
+  CK(h, cudaStreamSynchronize(h->stream));
+  uint8_t *h_sidx = (uint8_t *)h->h_stage;
+  RoundCtl ctl0; memset(&ctl0, 0, sizeof ctl0);
+  std::vector<int> set_idx(h->shapes.size(), -1);
+  int rc = EGS_OK;
+  int resolved = 0;
+
+  if (one_set) {
+    RoundDesc &rd = *R.h_rd; memset(&rd, 0, sizeof rd);
+    rd.ns = ns_cfg;
+    for (int q = 0; q < ns_cfg; q++) {
+      rd.slot[q] = batch_shapes[q]; set_idx[batch_shapes[q]] = q;
+      rd.reqs[q] = make_req(h->shapes[batch_shapes[q]].C, h->shapes[batch_shapes[q]].u);
+    }
+    for (int q = ns_cfg; q < RSMAX; q++) rd.slot[q] = -1;
+    for (int p = 0; p < P; p++) h_sidx[p] = (uint8_t)set_idx[slots[p]];
+    memset(h_sidx + P, 0xFF, 8);
+    ctl0.next_p = 0; ctl0.p_end = P;
+    *R.h_ctl = ctl0;
+    CK(h, cudaMemcpyAsync(R.d_rd, R.h_rd, sizeof(RoundDesc), cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(R.d_pod_sidx, h_sidx, (size_t)P + 8, cudaMemcpyHostToDevice, h->stream));
+    CK(h, cudaMemcpyAsync(R.d_ctl, R.h_ctl, sizeof(RoundCtl), cudaMemcpyHostToDevice, h->stream));
+    // rounds are enqueued in chunks; finished batches make the remaining launches of a chunk return at once
+    int chunk = h->timing ? 1 : 8;
+    int launched = 0;
+    while (true) {
+      for (int r = 0; r < chunk; r++) { rc = launch_round(); if (rc != EGS_OK) break; }
+      if (rc != EGS_OK) break;
+      launched += chunk;
+      rc = read_ctl();
+      if (rc != EGS_OK) break;
+      resolved = R.h_ctl->next_p;
+      if (R.h_ctl->error) { rc = fail(h, EGS_ERR_CUDA, "rounds: resolver made no progress"); break; }
+      if (resolved >= P) break;
+      if (!h->timing) {
+        const double per_round = std::max(1.0, (double)resolved / std::max(1, (int)R.h_ctl->rounds));
+        chunk = (int)std::min(256.0, std::max(4.0, (P - resolved) / per_round * 1.05 + 2.0));
+      }
+    }
+  } else {
+    // more distinct shapes than one set holds: the host forms the set of every round (one synchronisation per round)
+    int p0 = 0;
+    while (p0 < P) {
+      RoundDesc &rd = *R.h_rd; memset(&rd, 0, sizeof rd);
+      std::fill(set_idx.begin(), set_idx.end(), -1);
+      int n = 0, plim = p0;
+      for (; plim < P; plim++) {
+        const int slot = slots[plim];
+        if (set_idx[slot] < 0) {
+          if (n == RSMAX) break;
+          set_idx[slot] = n; rd.slot[n] = slot; rd.reqs[n] = make_req(h->shapes[slot].C, h->shapes[slot].u); n++;
+        }
+        h_sidx[plim] = (uint8_t)set_idx[slot];
+      }
+      rd.ns = n; ns_round = n;
+      for (int q = n; q < RSMAX; q++) rd.slot[q] = -1;
+      memset(h_sidx + plim, 0xFF, 8);
+      ctl0.next_p = p0; ctl0.p_end = plim; ctl0.rounds = 0;
+      *R.h_ctl = ctl0;
+      CK(h, cudaMemcpyAsync(R.d_rd, R.h_rd, sizeof(RoundDesc), cudaMemcpyHostToDevice, h->stream));
+      const int a0 = p0 & ~3;
+      CK(h, cudaMemcpyAsync(R.d_pod_sidx + a0, h_sidx + a0, (size_t)(plim - a0) + 8, cudaMemcpyHostToDevice, h->stream));
+      CK(h, cudaMemcpyAsync(R.d_ctl, R.h_ctl, sizeof(RoundCtl), cudaMemcpyHostToDevice, h->stream));
+      rc = launch_round(); if (rc != EGS_OK) break;
+      rc = read_ctl(); if (rc != EGS_OK) break;
+      if (R.h_ctl->error || R.h_ctl->next_p <= p0) { rc = fail(h, EGS_ERR_CUDA, "rounds: resolver made no progress"); break; }
+      R.rounds += 1; R.pods += R.h_ctl->next_p - p0; R.tracked += R.h_ctl->tracked;
+      for (int i = 0; i < 4; i++) R.stops[i] += R.h_ctl->stops[i];
+      p0 = R.h_ctl->next_p;
+      resolved = p0;
+    }
   }
+  if (one_set && R.h_ctl) {
+    R.rounds += R.h_ctl->rounds; R.pods += R.h_ctl->pods; R.tracked += R.h_ctl->tracked;
+    for (int i = 0; i < 4; i++) R.stops[i] += R.h_ctl->stops[i];
+  }
+  if (R.h_ctl) for (int i = 0; i < 16; i++) R.prof[i] += R.h_ctl->prof[i];
   if (h->timing) for (auto &e : ev) cudaEventDestroy(e);
+  *n_done = std::min(resolved, P);
+  // no OPT_NEW may outlive the batch -- also after an error, so that the handle stays consistent
   const int n = h->hi - h->lo;
   if (n > 0) k_rounds_finalize<<<(n + 255) / 256, 256, 0, h->stream>>>(tb, R.d_obs, h->lo, h->hi);   // a shard may be empty
   k_clear_u8<<<(R.obs_cap + 255) / 256, 256, 0, h->stream>>>(R.d_obs, R.obs_cap);
+  if (rc != EGS_OK) return rc;
   CK(h, cudaGetLastError());
   return EGS_OK;
 }

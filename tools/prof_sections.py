@@ -12,13 +12,10 @@ out = (C.c_longlong * 16)()
 e.L.egs_debug_resolve_prof.argtypes = [C.c_void_p, C.c_void_p]
 e.L.egs_debug_resolve_prof(e.h, out)
 v = [int(x) for x in out]
-skip = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-names = ["fast:precond", "fast:decide", "fast:hazard", "fast:commit", "gen:decide", "gen:commit"]
-tot = sum(v[:6])
-print(e.rounds_stats(), "resolve ms", e.profile_get(3)[1])
-for nme, x in zip(names, v[:6]):
-    print(f"  {nme:14s} {x/1e6:9.2f} Mcyc  {100*x/max(tot,1):5.1f}%")
-print(f"  fast iterations {v[6]}, pods committed by fast path {v[7]} (avg {v[7]/max(v[6],1):.2f} of W avg {v[8]/max(v[6],1):.2f}), general-path pods {v[9]}")
-n=max(v[11],1)
-print(f"  head-win events {v[11]}: wait {v[12]/n:.0f}  install {v[13]/n:.0f}  heads {v[14]/n:.0f}  prefetch {v[15]/n:.0f} cycles each")
-print(f"  cycles/pod fast {sum(v[:4])/max(v[7],1):.0f}   general {sum(v[4:6])/max(v[9],1):.0f}")
+print(e.rounds_stats(), "resolve ms", e.profile_get(3)[1], "select", e.profile_get(2)[1], "merge", e.profile_get(4)[1])
+fast, gen, hw = max(v[6], 1), max(v[9], 1), max(v[11], 1)
+print(f"pods: fast {v[6]} (head-wins {v[11]}), general {v[9]}")
+print(f"  per-pod cycles (summed over owner warps / pods): prepare {v[0]/(fast+gen):.0f}  wait {v[1]/(fast+gen):.0f}  post {v[3]/fast:.0f}")
+print(f"  ticket: fast tracked-win {v[2]/max(fast-hw,1):.0f}  fast head-win {v[5]/hw:.0f} (install {v[12]/hw:.0f}, heads {v[13]/hw:.0f})  general {v[4]/gen:.0f}")
+print(f"  fast decide part (ticket start -> winner known) {v[7]/fast:.0f}")
+print(f"  total ticket Mcyc {(v[2]+v[5]+v[4])/1e6:.1f} = {(v[2]+v[5]+v[4])/1.965e6:.1f} ms at 1.965 GHz")
