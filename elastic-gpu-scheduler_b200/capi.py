@@ -24,7 +24,7 @@ SYMBOLS = [
     "egs_create", "egs_destroy", "egs_last_error", "egs_status_string", "egs_unit_from_requests",
     "egs_node_set_allocatable", "egs_node_set", "egs_state_load", "egs_state_load_bulk", "egs_state_dump",
     "egs_state_snapshot", "egs_state_restore",
-    "egs_filter", "egs_score", "egs_bind", "egs_option_peek", "egs_pod_apply", "egs_node_replay_pod", "egs_pod_cancel",
+    "egs_filter", "egs_score", "egs_bind", "egs_option_peek", "egs_option_dump", "egs_pod_apply", "egs_node_replay_pod", "egs_pod_cancel",
     "egs_pod_known", "egs_pod_released", "egs_schedule_batch", "egs_schedule_batch_device",
     "egs_shard_set", "egs_shard_range", "egs_comm_unique_id", "egs_comm_init", "egs_profile_evaluate", "egs_profile_get",
     "egs_profile_reset", "egs_get_stream", "egs_rounds_stats", "egs_mix64",
@@ -50,6 +50,8 @@ def load(build: bool = True):
     if _lib is not None:
         return _lib
     path = _build.build_libegs() if build else _build.LIBEGS
+    if os.environ.get("EGS_LIB"):                       # experiments: an alternative build of the same sources
+        path = os.path.join(_build.LIBDIR, os.environ["EGS_LIB"])
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: the CUDA extension is required (no CPU fallback)")
     L = C.CDLL(path)
@@ -70,6 +72,7 @@ def load(build: bool = True):
     L.egs_score.argtypes = [vp, i32, vp, i32, vp, vp]
     L.egs_bind.argtypes = [vp, i32, i32, vp, u64, vp]
     L.egs_option_peek.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.egs_option_dump.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp]
     L.egs_pod_apply.argtypes = [vp, i32, i32, vp, vp, vp, u64]
     L.egs_node_replay_pod.argtypes = [vp, i32, i32, vp, vp, vp, u64]
     L.egs_pod_cancel.argtypes = [vp, i32, i32, vp, vp, vp, u64]
@@ -203,6 +206,14 @@ class Egs:
         if not valid.value:
             return None
         return masks_to_lists(masks, len(req)), score.value
+
+    def option_dump(self, req, node0: int = 0, n: Optional[int] = None):
+        """Option cache of request `req` on nodes [node0, node0+n): (state u8, score i32, alloc_mask u8[n,4])."""
+        n = self.max_nodes - node0 if n is None else n
+        st = np.zeros(max(n, 1), np.uint8); sc = np.zeros(max(n, 1), np.int32); am = np.zeros((max(n, 1), 4), np.uint8)
+        self._ck(self.L.egs_option_dump(self.h, len(req), _p(units_array(req)), node0, n, _p(st), _p(sc), _p(am)),
+                 "egs_option_dump")
+        return st[:n], sc[:n], am[:n]
 
     def pod_apply(self, node: int, req, alloc, uid: int) -> int:
         off, idx = _alloc_arrays(alloc)

@@ -607,6 +607,34 @@ extern "C" int egs_option_peek(egs_handle *h, int node_id, int n_containers, con
   return EGS_OK;
 }
 
+extern "C" int egs_option_dump(egs_handle *h, int n_containers, const egs_unit *units, int node0, int n,
+                               uint8_t *out_state, int32_t *out_score, uint8_t *out_alloc_mask) {
+  if (!h) return EGS_ERR_BAD_ARG;
+  Guard g(h);
+  if (node0 < 0 || n < 0 || node0 + n > h->max_nodes) return EGS_ERR_BAD_ARG;
+  int slot;
+  TRY(intern(h, n_containers, units, &slot));
+  if (n == 0) return EGS_OK;
+  const OptTable t = table(h, slot);
+  const size_t sn = (size_t)n;
+  TRY(ensure_stage(h, sn * (1 + 4 + EGS_C)));
+  CK(h, cudaStreamSynchronize(h->stream));
+  char *s = (char *)h->h_stage;
+  int32_t *hs = (int32_t *)s; uint8_t *hst = (uint8_t *)(hs + sn); uint8_t *hal = hst + sn;
+  CK(h, cudaMemcpyAsync(hs, t.sc + node0, 4 * sn, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaMemcpyAsync(hst, t.st + node0, sn, cudaMemcpyDeviceToHost, h->stream));
+  for (int c = 0; c < EGS_C; c++)
+    CK(h, cudaMemcpyAsync(hal + (size_t)c * sn, t.al + (size_t)c * t.plane + node0, sn, cudaMemcpyDeviceToHost, h->stream));
+  CK(h, cudaStreamSynchronize(h->stream));
+  for (size_t i = 0; i < sn; i++) {
+    const bool cached = hst[i] == OPT_CACHED;
+    if (out_state) out_state[i] = hst[i] == OPT_CACHED ? 1 : hst[i] == OPT_UNFIT ? 2 : 0;
+    if (out_score) out_score[i] = cached ? hs[i] : 0;
+    if (out_alloc_mask) for (int c = 0; c < EGS_C; c++) out_alloc_mask[i * EGS_C + c] = (cached && c < n_containers) ? hal[(size_t)c * sn + i] : 0;
+  }
+  return EGS_OK;
+}
+
 static int apply_lists(egs_handle *h, int cancel, int node_id, int C, const egs_unit *units,
                        const int32_t *alloc_off, const int32_t *alloc_idx) {
   ApplyArgs a; memset(&a, 0, sizeof a);

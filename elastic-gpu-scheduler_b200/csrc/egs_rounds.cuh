@@ -358,6 +358,24 @@ __global__ void __launch_bounds__(256) k_merge(MergeArgs a) {
 // --------------------------------------------------------------------------------------------
 // k_resolve_mw: one CTA, one owner warp per shape (shape index si is owned by warp si % nw)
 // --------------------------------------------------------------------------------------------
+#ifdef EGS_RESOLVE_PROF
+#define PROF_T(i) { long long now_ = clock64(); prof[i] += now_ - tprev; tprev = now_; }
+#define PROF_C(i, v) { prof[i] += (v); }
+#else
+#define PROF_T(i)
+#define PROF_C(i, v)
+#endif
+
+// max of a 64-bit key over the warp: two redux.sync steps on the halves; owner = lowest lane holding it
+__device__ __forceinline__ unsigned long long warp_max_key_fwd(unsigned long long mine, int &owner_lane) {
+  const unsigned hi = (unsigned)(mine >> 32);
+  const unsigned m1 = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned m2 = __reduce_max_sync(0xffffffffu, hi == m1 ? (unsigned)mine : 0u);
+  const unsigned long long win = ((unsigned long long)m1 << 32) | m2;
+  owner_lane = __ffs(__ballot_sync(0xffffffffu, mine == win)) - 1;
+  return win;
+}
+
 struct MwArgs {
   int32_t *core, *mem;              // write-back targets
   int lo, hi, policy, n_shards;
@@ -371,29 +389,63 @@ struct MwArgs {
   RoundCtl *ctl;
   int rke;                          // list entries per (shape, shard) held in shared memory
   int nw;                           // worker warps
+  int use_hpay;                     // shared memory holds one prefetched candidate payload per shape
+  int use_lmax;                     // shared memory holds the per-lane column maxima of tkey per shape
 };
 
 template <int NS, int NT>
 struct MwSmem {
   static constexpr int HS = 2 * NT;                        // open-addressed set of tracked node ids
+  // ---- owner-private per shape (only the owner warp of shape s touches row s; slots >= the owner's view of nT
+  //      are written by the warp that installs them, inside its ticket)
   unsigned long long tkey[NS][NT];   // cand_key of a tracked node's option when it is fit (CACHED/NEW), else 0
-  unsigned long long hkey[NS][RD];   // current head of each untracked list (0 = none)
+  unsigned long long hkey[NS][RD];   // current head of each untracked list (0 = none); may be STALE (see maintain_heads)
   unsigned long long afd[NS], asd[NS], bh[NS];             // aggregates; best head over the shards
-  unsigned long long fterm[NT], sbase[NT];                 // fit_term / score_base of each tracked slot's node
+  unsigned long long xbest[NS];      // best key among slots OTHER shapes installed since the owner's last ticket
   uint32_t al[NS][NT];               // option.Allocated masks
   unsigned pmask[NS][NT / 32];       // tracked slots whose option is ABSENT: Trade at the shape's next pod
-  int afit[NS], bh_d[NS], dry[NS], observed[NS];
+  int afit[NS], bh_d[NS], dry[NS], observed[NS], xbest_t[NS], hv_nT[NS], hpay_node[NS];
+  int lm_seen[NS];                   // lmax[s] covers the slots [0, lm_seen[s]); -1: to be rebuilt
   int pu[NS];                        // summary of pmask[s]: -1 none, t >= 0 exactly slot t, -2 unknown / several
   int rq_single[NS], rq_core[NS], rq_mem[NS]; uint32_t rq_cmask[NS];
-  int node[NT], mt[NT], dirty[NT];
-  int rc[NT][EGS_G], rm[NT][EGS_G];
-  int hset[HS];
-  Req reqs[NS];
   uint8_t st[NS][NT];                // OPT_*
   uint8_t cur[NS][RD], len[NS][RD], more[NS][RD];
-  int turn, stop, stop_reason, nT, n_observed, mono, p0, p_end;
+  Req reqs[NS];
+  // ---- shared, changed only inside a ticket
+  unsigned long long fterm[NT], sbase[NT];                 // fit_term / score_base of each tracked slot's node
+  int node[NT], mt[NT], dirty[NT];
+  int ver[NT];                       // seqlock of the slot's rows: odd while a bind is writing them, +2 per bind
+  int rc[NT][EGS_G], rm[NT][EGS_G];
+  int hset[HS];
+  unsigned long long mbar[MW_MAX_WARPS];   // one per owner warp: "the ticket is yours"
+  int turn;                                // the pod whose ticket is open; MW_STOP | p once the round was stopped before pod p
+  int stop, stop_reason, stop_p, nT, n_observed, mono, p0, p_end;
 };
+#define MW_STOP 0x40000000
+#ifndef MW_POLL
+#define MW_POLL 0
+#endif
+#define MW_LA 3                            // an owner is woken (mbarrier) when the ticket is MW_LA pods before its pod
 
+// Ticket hand-over in two levels.  (1) `turn` in shared memory: the holder of pod p's ticket stores p+1 after its last
+// row store (same lane, program order; shared memory is one in-order unit per SM) and the owner of p+1 sees it on
+// its next poll -- no fence and no release/acquire instruction on the critical path.  (2) Only the owners of the
+// next MW_LA pods poll; everybody further away sleeps in hardware on its own mbarrier (try_wait suspends the
+// warp) and is woken by the owner of pod p - MW_LA right after that one handed its ticket on, i.e. by a warp that
+// is no longer on the critical path.  Polling by 16 warps steals issue slots from the ticket holder; an mbarrier
+// arrive with release semantics on the critical path costs several hundred cycles -- both measured.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {   // release.cta
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned parity) {   // acquire.cta
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
 
@@ -404,56 +456,46 @@ __device__ __forceinline__ unsigned hset_slot(uint32_t node) {
 template <class SM>
 __device__ __forceinline__ bool hset_has(const SM &S, uint32_t node) {
   for (unsigned i = hset_slot<SM>(node);; i = (i + 1) & (unsigned)(SM::HS - 1)) {
-    const int v = S.hset[i];
+    const int v = ld_vol(&S.hset[i]);
     if (v == (int)node) return true;
     if (v < 0) return false;
   }
 }
 template <class SM>
-__device__ __forceinline__ void hset_add(SM &S, uint32_t node) {   // one lane; at most NT entries (load <= 1/2)
+__device__ __forceinline__ void hset_add(SM &S, uint32_t node) {   // one lane, inside a ticket; at most NT entries (load <= 1/2)
   unsigned i = hset_slot<SM>(node);
   while (S.hset[i] >= 0) i = (i + 1) & (unsigned)(SM::HS - 1);
-  S.hset[i] = (int)node;
+  st_vol(&S.hset[i], (int)node);
 }
-// advance list (s, d) past entries whose node is tracked by now, and cache its head
+
+// The untracked candidate lists of shape s belong to its owner warp and are maintained LAZILY, outside the ticket:
+// entries whose node is tracked by now are skipped.  A head may therefore be STALE (its node became tracked after
+// this ran) -- harmless in the FAST regime (monotone round, every shape observed): only the owner itself changes
+// the tracked options of its shape, so that node's tracked option still carries the very same key, max(tracked) >=
+// stale head, and the stale head can never win; a head that does win is untracked, hence valid.  Outside the fast
+// regime (not-yet-observed NEW options are voided by other shapes' binds) general_pod re-validates the heads inside
+// the ticket (force).  Lanes d < D work on list (s, d).
 template <class SM>
-__device__ __forceinline__ void list_head_update(SM &S, const unsigned long long *lk, int D, int rke, int s, int d) {
-  int c = S.cur[s][d];
-  const int len = S.len[s][d];
-  unsigned long long k = 0;
-  const unsigned long long *l = lk + ((size_t)s * D + d) * rke;
-  while (c < len) { k = l[c]; if (!hset_has(S, key_node(k))) break; c++; }
-  S.cur[s][d] = (uint8_t)c;
-  S.hkey[s][d] = c < len ? k : 0ull;
-}
-// best head of shape s over the shards, and whether a truncated list ran dry (one lane)
-template <class SM>
-__device__ __forceinline__ void best_head_update(SM &S, int D, int s) {
-  unsigned long long b = 0; int bd = 0, dry = 0;
-  for (int d = 0; d < D; d++) {
-    const unsigned long long k = S.hkey[s][d];
-    if (k > b) { b = k; bd = d; }
-    dry |= (k == 0 && S.more[s][d] != 0);
+__device__ __forceinline__ void maintain_heads(SM &S, const unsigned long long *lk, int D, int rke, int s, int lane, bool force) {
+  const int nT = ld_vol(&S.nT);
+  if (!force && S.hv_nT[s] == nT) return;                       // no node became tracked since the last look
+  unsigned long long k = 0; int dryl = 0;
+  if (lane < D) {
+    const int d = lane;
+    int c = S.cur[s][d];
+    const int len = S.len[s][d];
+    const unsigned long long *l = lk + ((size_t)s * D + d) * rke;
+    while (c < len) { k = l[c]; if (!hset_has(S, key_node(k))) break; c++; }
+    if (c >= len) k = 0;
+    S.cur[s][d] = (uint8_t)c;
+    S.hkey[s][d] = k;
+    dryl = (k == 0 && S.more[s][d] != 0);
   }
-  S.bh[s] = b; S.bh_d[s] = bd; S.dry[s] = dry;
-}
-
-#ifdef EGS_RESOLVE_PROF
-#define PROF_T(i) { long long now_ = clock64(); prof[i] += now_ - tprev; tprev = now_; }
-#define PROF_C(i, v) { prof[i] += (v); }
-#else
-#define PROF_T(i)
-#define PROF_C(i, v)
-#endif
-
-__device__ __forceinline__ unsigned long long warp_max_key(unsigned long long mine, int &owner_lane) {
-  // max of a 64-bit key over the warp: two redux.sync steps on the halves; owner = lowest lane holding it
-  const unsigned hi = (unsigned)(mine >> 32);
-  const unsigned m1 = __reduce_max_sync(0xffffffffu, hi);
-  const unsigned m2 = __reduce_max_sync(0xffffffffu, hi == m1 ? (unsigned)mine : 0u);
-  const unsigned long long win = ((unsigned long long)m1 << 32) | m2;
-  owner_lane = __ffs(__ballot_sync(0xffffffffu, mine == win)) - 1;
-  return win;
+  int owner;
+  const unsigned long long b = warp_max_key_fwd(k, owner);
+  const unsigned anydry = __ballot_sync(0xffffffffu, dryl);
+  if (lane == 0) { S.bh[s] = b; S.bh_d[s] = b ? owner : 0; S.dry[s] = anydry != 0; S.hv_nT[s] = nT; }
+  __syncwarp();
 }
 
 // Trade of one fractional single-container request on a tracked node, one lane per GPU (lane & 7), every
@@ -474,16 +516,17 @@ __device__ __forceinline__ int trade_lanes(const int (&c)[EGS_G], const int (&m)
   return __reduce_max_sync(0xffffffffu, key);
 }
 
-// A slot becomes tracked: install the payload of candidate `cd` (node w) as tracked slot t.  All lanes.
+// A node becomes tracked: install the payload `cd` (node w) as slot t.  All lanes, inside the ticket of shape s_self.
+// Other shapes learn about the slot through xbest (their owners scan only the slots they have seen).
 template <class SM>
-__device__ __forceinline__ void install_slot(SM &S, const MwArgs &a, const char *cd, int t, uint32_t w, int ns, int lane) {
+__device__ __noinline__ void install_slot(SM &S, const MwArgs &a, const char *cd, int t, uint32_t w, int ns, int s_self, int lane) {
   const int nsc = a.L.nsc;
   if (lane < 2 * EGS_G) {
     const int v = reinterpret_cast<const int *>(cd + CD_RC)[lane];          // rc[8], rm[8] contiguous
     if (lane < EGS_G) S.rc[t][lane] = v; else S.rm[t][lane - EGS_G] = v;
   }
   if (lane == 0) {
-    S.node[t] = (int)w; S.mt[t] = *reinterpret_cast<const int *>(cd + CD_MT); S.dirty[t] = 0;
+    S.node[t] = (int)w; S.mt[t] = *reinterpret_cast<const int *>(cd + CD_MT); S.dirty[t] = 0; S.ver[t] = 0;
     S.fterm[t] = *reinterpret_cast<const unsigned long long *>(cd + CD_FT);
     S.sbase[t] = *reinterpret_cast<const unsigned long long *>(cd + CD_SB);
     hset_add(S, w);
@@ -494,34 +537,33 @@ __device__ __forceinline__ void install_slot(SM &S, const MwArgs &a, const char 
   for (int s2 = lane; s2 < ns; s2 += 32) {
     uint8_t st = cst[s2];
     if (st == OPT_NEW && S.observed[s2]) st = OPT_CACHED;
-    S.st[s2][t] = st; S.al[s2][t] = cal[s2];
-    S.tkey[s2][t] = (st == OPT_CACHED || st == OPT_NEW) ? cand_key(csc[s2], w) : 0ull;
+    const unsigned long long k = (st == OPT_CACHED || st == OPT_NEW) ? cand_key(csc[s2], w) : 0ull;
+    S.st[s2][t] = st; S.al[s2][t] = cal[s2]; S.tkey[s2][t] = k;
+    if (s2 != s_self && k > S.xbest[s2]) { S.xbest[s2] = k; S.xbest_t[s2] = t; }
     if (st == OPT_ABSENT) { atomicOr(&S.pmask[s2][t >> 5], 1u << (t & 31)); S.pu[s2] = -2; }   // select leaves none; kept for safety
   }
 }
 
-// the lists whose HEAD is node w advance now (entries deeper in a list are skipped when they surface)
+// payload of the current best head of shape s: prefetched copy in shared memory, else the candidate buffer
 template <class SM>
-__device__ __forceinline__ void heads_drop_node(SM &S, const unsigned long long *lk, int D, int rke, int ns, uint32_t w, int lane) {
-  for (int i = lane; i < ns * D; i += 32) {
-    const int s2 = i / D, d2 = i % D;
-    const unsigned long long hk = S.hkey[s2][d2];
-    if (hk != 0 && key_node(hk) == w) list_head_update(S, lk, D, rke, s2, d2);
-  }
-  __syncwarp();
-  for (int s2 = lane; s2 < ns; s2 += 32) best_head_update(S, D, s2);
+__device__ __forceinline__ const char *head_payload(const SM &S, const MwArgs &a, const char *hpay, int s, uint32_t w) {
+  if (hpay && S.hpay_node[s] == (int)w) return hpay + (size_t)s * a.L.cand_bytes;
+  const int d = S.bh_d[s];
+  return a.bufs + (size_t)d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + S.cur[s][d]) * a.L.cand_bytes;
 }
 
 // ---- general pod (inside the ticket, whole warp): any shape, any number of pending options, any regime.
 // Returns 0, or the stop reason (nothing was changed for this pod then).
 template <class SM>
-__device__ int general_pod(SM &S, const MwArgs &a, const unsigned long long *lk, int lane, int p, int s, int ns, int D, int rke) {
+__device__ __noinline__ int general_pod(SM &S, const MwArgs &a, const unsigned long long *lk, const char *hpay, int lane, int p, int s, int ns) {
   const int grp = lane >> 3, gl = lane & 7;
   const unsigned gmask = 0xFFu << (8 * grp);
   const bool mono = S.mono != 0;
   int nT = S.nT;
   if (nT >= SM::HS / 2) return 2;                               // no free tracked slot for a new winner
+  maintain_heads(S, lk, a.n_shards, a.rke, s, lane, true);      // inside the ticket the tracked set is exact
   if (S.dry[s]) return 3;                                       // a truncated list ran dry: next round
+  if (lane == 0) { S.xbest[s] = 0; S.xbest_t[s] = -1; S.lm_seen[s] = -1; }   // the scan below sees every slot; column maxima are rebuilt later
   if (!S.observed[s]) {                                         // first pod of this shape in the round:
     for (int t = lane; t < nT; t += 32) if (S.st[s][t] == OPT_NEW) S.st[s][t] = OPT_CACHED;   // NEW options are now ordinary
     __syncwarp();
@@ -597,9 +639,9 @@ __device__ int general_pod(SM &S, const MwArgs &a, const unsigned long long *lk,
     if (k > best) { best = k; best_t = t; }
   }
   __syncwarp();
-  // winner = max over (tracked options, best untracked list head)
+  // winner = max over (tracked options, best untracked list head); a stale head never exceeds the tracked maximum
   int owner;
-  const unsigned long long tbest = warp_max_key(best, owner);
+  const unsigned long long tbest = warp_max_key_fwd(best, owner);
   const int tw0 = __shfl_sync(0xffffffffu, best_t, owner);
   const unsigned long long head = S.bh[s];
   const bool from_head = head > tbest;
@@ -615,14 +657,13 @@ __device__ int general_pod(SM &S, const MwArgs &a, const unsigned long long *lk,
       // an untracked node wins: it becomes tracked
       t = nT;
       const uint32_t w = key_node(win);
-      const int d = S.bh_d[s];
-      const char *cd = a.bufs + (size_t)d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + S.cur[s][d]) * a.L.cand_bytes;
-      install_slot(S, a, cd, t, w, ns, lane);
+      asm volatile("cp.async.wait_all;" ::: "memory");
       __syncwarp();
-      heads_drop_node(S, lk, D, rke, ns, w, lane);
+      install_slot(S, a, head_payload(S, a, hpay, s, w), t, w, ns, s, lane);
       __syncwarp();
       nT = t + 1;
-      if (lane == 0) { __threadfence_block(); S.nT = nT; }
+      if (lane == 0) { __threadfence_block(); st_vol(&S.nT, nT); }
+      __syncwarp();
     }
     o_node = S.node[t];
     const uint32_t masks = S.al[s][t] & S.rq_cmask[s];
@@ -640,14 +681,16 @@ __device__ int general_pod(SM &S, const MwArgs &a, const unsigned long long *lk,
       if (lane == 0) {
         S.st[s][t] = OPT_ABSENT; S.tkey[s][t] = 0; S.pmask[s][t >> 5] = npm;
         S.afit[s] = nfit; S.afd[s] = nfd; S.asd[s] = nsd; S.dirty[t] = 1;
-        if (ok) { S.rc[t][g] = c - rc; S.rm[t][g] = m - rm; }
+        if (ok) { const int v = S.ver[t]; st_vol(&S.ver[t], v + 1); S.rc[t][g] = c - rc; S.rm[t][g] = m - rm; st_vol(&S.ver[t], v + 2); }
       }
     } else {
       __syncwarp();
       if (lane == 0) {
         S.st[s][t] = OPT_ABSENT; S.tkey[s][t] = 0; S.pmask[s][t >> 5] = npm;
         S.afit[s] = nfit; S.afd[s] = nfd; S.asd[s] = nsd; S.dirty[t] = 1;
+        const int v = S.ver[t]; st_vol(&S.ver[t], v + 1);
         ok = transact_row(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], masks) ? 1 : 0;
+        st_vol(&S.ver[t], v + 2);
       }
       ok = __shfl_sync(0xffffffffu, ok, 0);
     }
@@ -664,6 +707,8 @@ __device__ int general_pod(SM &S, const MwArgs &a, const unsigned long long *lk,
           const unsigned long long k2 = S.tkey[s2][t];
           S.st[s2][t] = OPT_ABSENT; S.tkey[s2][t] = 0; S.pmask[s2][t >> 5] |= pbit; S.pu[s2] = -2;
           S.afit[s2] -= 1; S.afd[s2] -= S.fterm[t]; S.asd[s2] -= score_term_b(S.sbase[t], key_score(k2));
+          if (S.xbest_t[s2] == t) { S.xbest[s2] = 0; S.xbest_t[s2] = -1; }   // (an unobserved shape rescans anyway)
+          S.lm_seen[s2] = -1;
         }
       }
     }
@@ -689,15 +734,20 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = MwSmem<NS, NT>;
   SM &S = *reinterpret_cast<SM *>(smem_raw);
-  unsigned long long *lk = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15));   // [ns][D][rke]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
   const int D = a.n_shards, rke = a.rke, nw = a.nw;
   const int ns = a.rd->ns;
+  unsigned long long *lk = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15));   // [ns][D][rke]
+  char *hpay = a.use_hpay ? reinterpret_cast<char *>(lk + (size_t)ns * D * rke) : nullptr;                        // [ns][cand_bytes]
+  // column maxima of tkey: lane L keeps max over the slots t = L (mod 32) of its shapes -> the owner's scan is 1 load
+  unsigned long long *lmax = a.use_lmax ? reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15) + (size_t)ns * D * rke * 8 + (a.use_hpay ? (size_t)ns * a.L.cand_bytes : 0)) : nullptr;   // [ns][32]
+  int *lmax_t = lmax ? reinterpret_cast<int *>(lmax + (size_t)ns * 32) : nullptr;                                 // [ns][32]
   // ---- prologue
   {
     int p0 = a.p0, p_end = a.p_limit;
     if (a.p0 < 0) { if (ctl_idle(a.ctl)) return; p0 = a.ctl->next_p; p_end = a.ctl->p_end; }
-    if (tid == 0) { S.p0 = p0; S.p_end = p_end; S.turn = p0; S.stop = 0; S.stop_reason = 0; S.nT = 0; S.n_observed = 0; }
+    if (tid == 0) { S.p0 = p0; S.p_end = p_end; S.turn = p0; S.stop = 0; S.stop_reason = 0; S.stop_p = p_end; S.nT = 0; S.n_observed = 0; }
+    if (tid < MW_MAX_WARPS) mbar_init(&S.mbar[tid], 1);
   }
   for (int i = tid; i < SM::HS; i += nthreads) S.hset[i] = -1;
   for (int i = tid; i < NS * (NT / 32); i += nthreads) (&S.pmask[0][0])[i] = 0;
@@ -714,9 +764,11 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
         sd += reinterpret_cast<const unsigned long long *>(b + a.L.off_sd)[s];
         if (len > rke) { len = rke; more = 1; }                  // the part of the list held in shared memory
       }
-      S.cur[s][d] = 0; S.len[s][d] = (uint8_t)len; S.more[s][d] = (uint8_t)more;
+      S.cur[s][d] = 0; S.len[s][d] = (uint8_t)len; S.more[s][d] = (uint8_t)more; S.hkey[s][d] = 0;
     }
     S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd; S.observed[s] = 0; S.pu[s] = -1;
+    S.xbest[s] = 0; S.xbest_t[s] = -1; S.hv_nT[s] = -1; S.hpay_node[s] = -1; S.bh[s] = 0; S.bh_d[s] = 0; S.dry[s] = 0;
+    S.lm_seen[s] = -1;
     if (s < ns) {
       S.reqs[s] = a.rd->reqs[s];
       const Req &r = a.rd->reqs[s];
@@ -735,9 +787,6 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
     for (int s = 0; s < ns; s++) for (int c = 0; c < S.reqs[s].C; c++) mono &= S.reqs[s].core[c] >= 0 && S.reqs[s].mem[c] >= 0;
     S.mono = mono ? 1 : 0;
   }
-  for (int i = tid; i < ns * D; i += nthreads) list_head_update(S, lk, D, rke, i / D, i % D);
-  __syncthreads();
-  for (int s = tid; s < ns; s += nthreads) best_head_update(S, D, s);
   __syncthreads();
   const int p0 = S.p0, p_end = S.p_end;
 #ifdef EGS_RESOLVE_PROF
@@ -749,11 +798,17 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
     int cb = p0 & ~3;                                            // chunk base (multiple of 4)
     unsigned pm[4] = {0, 0, 0, 0};                               // per j: lanes whose pod 4*lane+j is mine
     uint32_t myword = 0;
+    uint32_t nextword = 0xFFFFFFFFu, prevword = 0xFFFFFFFFu;     // shape indices of pods cb+128..cb+131 / cb-4..cb-1
+    unsigned ph = 0;                                             // phase parity of my mbarrier
     auto load_chunk = [&](int base) {
       const int q = base + 4 * lane;
       uint32_t wd = 0xFFFFFFFFu;
       if (q < p_end) wd = *reinterpret_cast<const uint32_t *>(a.pod_sidx + q);   // padded allocation: reads up to 3 past the end
       myword = wd;
+      uint32_t nx = 0xFFFFFFFFu, pv = 0xFFFFFFFFu;
+      if (lane == 0 && base + 128 < p_end) nx = *reinterpret_cast<const uint32_t *>(a.pod_sidx + base + 128);
+      if (lane == 0 && base >= 4) pv = *reinterpret_cast<const uint32_t *>(a.pod_sidx + base - 4);
+      nextword = __shfl_sync(0xffffffffu, nx, 0); prevword = __shfl_sync(0xffffffffu, pv, 0);
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         const int si = (wd >> (8 * j)) & 0xFF;
@@ -762,10 +817,18 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
       }
     };
     load_chunk(cb);
+    // owner of pod cb + i (i in [-4, 131]); -1 outside [p0, p_end).  Warp-uniform, all lanes call it.
+    auto owner_rel = [&](int i) -> int {
+      const uint32_t wd = __shfl_sync(0xffffffffu, myword, (i >> 2) & 31);
+      const uint32_t x = i < 0 ? prevword : i >= 128 ? nextword : wd;
+      const int si = (int)((x >> (8 * (i & 3))) & 0xFFu);
+      return (cb + i >= p0 && cb + i < p_end && si < ns) ? si % nw : -1;
+    };
     const bool mono = S.mono != 0;
+    const int gl = lane & 7;
     while (true) {
       // next own pod
-      int p = -1, s = 0;
+      int p = -1, s = 0, wake = -1; bool sleep_first = false;
       while (true) {
         int best_i = 1 << 30;
 #pragma unroll
@@ -775,6 +838,21 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
           pm[j] &= ~(1u << l);
           p = cb + best_i;
           s = (__shfl_sync(0xffffffffu, myword, l) >> (8 * j)) & 0xFF;
+          // whom do I wake after my ticket (the owner of p + MW_LA, unless it is awake anyway: it owns one of the pods
+          // p .. p + MW_LA - 1), and do I sleep before polling (same rule seen from the other side)?
+#if MW_POLL
+          wake = owner_rel(best_i + MW_LA);
+          sleep_first = p - MW_LA >= p0;
+#pragma unroll
+          for (int k = 1; k <= MW_LA; k++) {
+            if (k < MW_LA && owner_rel(best_i + k) == wake) wake = -1;
+            if (owner_rel(best_i - k) == warp) sleep_first = false;
+          }
+#else
+          wake = owner_rel(best_i + 1);                           // the next owner sleeps on its mbarrier until I arrive
+          sleep_first = p > p0 && owner_rel(best_i - 1) != warp;  // exactly one arrive per wait
+#endif
+          if (wake == warp) wake = -1;
           break;
         }
         cb += 128;
@@ -782,132 +860,170 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
         load_chunk(cb);
       }
       if (p < 0) break;
-      // ---- preparation outside the ticket (only owner-private data): best tracked option of s
-      const bool fast = mono && S.rq_single[s] && ld_vol(&S.n_observed) == ns;
-      unsigned long long pre_best = 0; int pre_t = -1, pre_nT = 0;
+      // ======== preparation outside the ticket: only owner-private data and data that never changes
+      maintain_heads(S, lk, D, rke, s, lane, false);
+      const unsigned long long head = S.bh[s];
+      if (hpay && head != 0 && S.hpay_node[s] != (int)key_node(head)) {   // payload of the best head -> shared memory,
+        const int d = S.bh_d[s];                                          // asynchronously: only a head-win waits for it
+        const char *src = a.bufs + (size_t)d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + S.cur[s][d]) * a.L.cand_bytes;
+        char *dst = hpay + (size_t)s * a.L.cand_bytes;
+        if (a.use_hpay == 2) {
+          asm volatile("cp.async.wait_all;" ::: "memory");                // an older copy into this buffer has long landed
+          for (int i = lane; i < a.L.cand_bytes / 16; i += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst + i * 16)), "l"(src + i * 16) : "memory");
+          asm volatile("cp.async.commit_group;" ::: "memory");
+        } else {
+          for (int i = lane; i < a.L.cand_bytes / 16; i += 32) reinterpret_cast<int4 *>(dst)[i] = reinterpret_cast<const int4 *>(src)[i];
+        }
+        if (lane == 0) S.hpay_node[s] = (int)key_node(head);
+        __syncwarp();
+      }
+      const int pu = S.pu[s];
+      const bool fast = mono && S.rq_single[s] && pu != -2 && ld_vol(&S.n_observed) == ns;
+      // fast pods: the best tracked option of s over the slots seen so far, and everything the ticket will need
+      unsigned long long pre_best = 0; int pre_t = -1;
+      const int u = pu, uu = max(pu, 0);
+      uint32_t und = 0, pre_al = 0; unsigned long long ft_u = 0, sb_u = 0, afd = 0, asd = 0;
+      int rq_c = 0, rq_m = 0, afit = 0, dry = 0, v_pre = -1, bk_pre = -1;
       if (fast) {
-        pre_nT = ld_vol(&S.nT);
+        const int pre_nT = ld_vol(&S.nT);
         __threadfence_block();
         unsigned long long b = 0; int bt = -1;
-        for (int t = lane; t < pre_nT; t += 32) { const unsigned long long k = S.tkey[s][t]; if (k > b) { b = k; bt = t; } }
+        const int seen = lmax ? S.lm_seen[s] : -1;
+        if (seen < 0) {                                           // (re)build: lane L scans its column t = L, L+32, ...
+#pragma unroll 4
+          for (int t = lane; t < pre_nT; t += 32) { const unsigned long long k = S.tkey[s][t]; if (k > b) { b = k; bt = t; } }
+        } else {                                                  // cached column maxima + the slots installed since
+          b = lmax[s * 32 + lane]; bt = lmax_t[s * 32 + lane];
+          for (int t = seen + ((lane - seen) & 31); t < pre_nT; t += 32) { const unsigned long long k = S.tkey[s][t]; if (k > b) { b = k; bt = t; } }
+        }
+        if (lmax) { lmax[s * 32 + lane] = b; lmax_t[s * 32 + lane] = bt; if (lane == 0) S.lm_seen[s] = pre_nT; }
         int owner;
-        pre_best = warp_max_key(b, owner);
+        pre_best = warp_max_key_fwd(b, owner);
         pre_t = __shfl_sync(0xffffffffu, bt, owner);
+        pre_al = pre_t >= 0 ? (S.al[s][pre_t] & 0xFFu) : 0u;
+        und = (uint32_t)S.node[uu]; ft_u = S.fterm[uu]; sb_u = S.sbase[uu];
+        rq_c = S.rq_core[s]; rq_m = S.rq_mem[s];
+        afit = S.afit[s]; afd = S.afd[s]; asd = S.asd[s]; dry = S.dry[s];
+        if (u >= 0) {                                             // Trade of the pending option on the rows as they are NOW;
+          v_pre = ld_vol(&S.ver[uu]);                             // the ticket reuses it when no bind touched the node since
+          int c[EGS_G], m[EGS_G];
+#pragma unroll
+          for (int g = 0; g < EGS_G; g++) { c[g] = ld_vol(&S.rc[uu][g]); m[g] = ld_vol(&S.rm[uu][g]); }
+          bk_pre = trade_lanes(c, m, gl, rq_c, rq_m, a.policy);
+          if ((v_pre & 1) || ld_vol(&S.ver[uu]) != v_pre) v_pre = -1;   // a bind was writing the rows meanwhile
+        }
       }
       PROF_T(0)
-      // ---- wait for the ticket
+      // ======== the ticket
       bool stopped = false;
-      while (true) {
+#if MW_POLL
+      if (sleep_first) {                                          // far from my turn: sleep until the ticket is MW_LA pods away
+        while (!mbar_try_wait(&S.mbar[warp], ph)) { if (ld_vol(&S.turn) & MW_STOP) { stopped = true; break; } }
+        ph ^= 1u;
+      }
+      while (!stopped) {
         const int t = ld_vol(&S.turn);
         if (t == p) break;
-        if (ld_vol(&S.stop)) { stopped = true; break; }
-        if (p - t > 6) __nanosleep(200);
+        if (t & MW_STOP) stopped = true;
       }
+#else
+      if (sleep_first) {                                          // else: I still hold the ticket
+        while (!mbar_try_wait(&S.mbar[warp], ph)) { if (ld_vol(&S.turn) & MW_STOP) { stopped = true; break; } }
+        ph ^= 1u;
+        if (ld_vol(&S.turn) & MW_STOP) stopped = true;
+      }
+#endif
       if (stopped) break;
-      __threadfence_block();
       PROF_T(1)
       int reason = 0;
-      const int pu = S.pu[s];
-      if (fast && pu != -2) {
-        // ================= fast pod: single-container shape, monotone round, every shape observed, <= 1 pending
-        const int nT = S.nT;
-        const int u = pu, uu = max(u, 0);
-        const int gl = lane & 7;
-        const int4 c0 = *reinterpret_cast<const int4 *>(&S.rc[uu][0]), c1 = *reinterpret_cast<const int4 *>(&S.rc[uu][4]);
-        const int4 m0 = *reinterpret_cast<const int4 *>(&S.rm[uu][0]), m1 = *reinterpret_cast<const int4 *>(&S.rm[uu][4]);
-        const uint32_t und = (uint32_t)S.node[uu];
-        const unsigned long long head = S.bh[s];
-        const int dry = S.dry[s];
-        const int rq_c = S.rq_core[s], rq_m = S.rq_mem[s];
-        unsigned long long best = pre_best; int best_t = pre_t;
-        if (nT > pre_nT) {                                        // slots installed by other shapes since the preparation
-          if (nT - pre_nT <= 4) {
-            for (int t = pre_nT; t < nT; t++) { const unsigned long long k = S.tkey[s][t]; if (k > best) { best = k; best_t = t; } }
-          } else {
-            unsigned long long b = 0; int bt = -1;
-            for (int t = pre_nT + lane; t < nT; t += 32) { const unsigned long long k = S.tkey[s][t]; if (k > b) { b = k; bt = t; } }
-            int owner;
-            const unsigned long long xb = warp_max_key(b, owner);
-            const int xt = __shfl_sync(0xffffffffu, bt, owner);
-            if (xb > best) { best = xb; best_t = xt; }
-          }
-        }
-        int bk = -1;
-        if (u >= 0) {
+      if (fast) {
+        // ---- fast pod: single-container shape, monotone round, every shape observed, at most one pending option
+        const unsigned long long xb = S.xbest[s];
+        const int xt = S.xbest_t[s];
+        int bk = bk_pre;
+        if (u >= 0 && S.ver[uu] != v_pre) {                       // the node's rows changed since the preparation
+          const int4 c0 = *reinterpret_cast<const int4 *>(&S.rc[uu][0]), c1 = *reinterpret_cast<const int4 *>(&S.rc[uu][4]);
+          const int4 m0 = *reinterpret_cast<const int4 *>(&S.rm[uu][0]), m1 = *reinterpret_cast<const int4 *>(&S.rm[uu][4]);
           const int c[EGS_G] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
           const int m[EGS_G] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
           bk = trade_lanes(c, m, gl, rq_c, rq_m, a.policy);
+          PROF_C(14, 1)
         }
+#ifdef EGS_RESOLVE_PROF
+        long long q1_ = clock64() + (bk & 0);
+#endif
         const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
         const unsigned long long tradekey = bk >= 0 ? cand_key(sc, und) : 0ull;
-        if (tradekey > best) { best = tradekey; best_t = u; }
+        unsigned long long best = pre_best; int tw = pre_t; uint32_t masks = pre_al;
+        if (xb > best) { best = xb; tw = xt; masks = 0; }
+        if (tradekey > best) { best = tradekey; tw = u; masks = 1u << (bk & 7); }
         const bool from_head = head > best;
         const unsigned long long win = from_head ? head : best;
-#ifdef EGS_RESOLVE_PROF
-        { const long long n_ = clock64(); prof[7] += n_ - tprev; }
-#endif
+        int nT = 0;
         if (dry) reason = 3;
-        else if (win != 0 && from_head && nT >= NT) reason = 2;
+        else if (from_head) { nT = S.nT; if (nT >= NT) reason = 2; }
+#ifdef EGS_RESOLVE_PROF
+        long long q2_ = clock64() + (reason & 0) + ((int)win & 0);
+        long long q3_ = q2_;
+#endif
         if (reason == 0) {
-          // the shape's aggregates after this pod's filter
-          const int fit = S.afit[s] + (bk >= 0);
-          const unsigned long long fd = S.afd[s] + (bk >= 0 ? S.fterm[uu] : 0ull);
-          const unsigned long long sd = S.asd[s] + (bk >= 0 ? score_term_b(S.sbase[uu], sc) : 0ull);
           int o_node = -1, o_status = EGS_ERR_NOFIT; uint32_t o_masks = 0;
-          int tw = -1;
           if (win != 0) {
-            tw = best_t;
-            uint32_t masks;
             if (from_head) {
               tw = nT;
               const uint32_t w = key_node(win);
-              const int d = S.bh_d[s];
-              const char *cd = a.bufs + (size_t)d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + S.cur[s][d]) * a.L.cand_bytes;
-#ifdef EGS_RESOLVE_PROF
-              const long long i0_ = clock64();
-#endif
-              install_slot(S, a, cd, tw, w, ns, lane);
+              asm volatile("cp.async.wait_all;" ::: "memory");
               __syncwarp();
-#ifdef EGS_RESOLVE_PROF
-              const long long i1_ = clock64();
-#endif
-              heads_drop_node(S, lk, D, rke, ns, w, lane);
+              install_slot(S, a, head_payload(S, a, hpay, s, w), tw, w, ns, s, lane);
               __syncwarp();
-#ifdef EGS_RESOLVE_PROF
-              { const long long i2_ = clock64(); prof[12] += i1_ - i0_; prof[13] += i2_ - i1_; }
-#endif
               masks = S.al[s][tw] & 0xFFu;
               PROF_C(11, 1)
-            } else {
-              masks = (tw == u) ? (1u << (bk & 7)) : (S.al[s][tw] & 0xFFu);
+            } else if (masks == 0) {
+              masks = S.al[s][tw] & 0xFFu;                        // a slot another shape installed
             }
             const int g = __ffs(masks) - 1;
             const int cc = S.rc[tw][g], mm = S.rm[tw][g];
             const int ok = (cc >= rq_c && mm >= rq_m) ? 1 : 0;    // GPUs.Transact gpu.go:164-171
             o_node = S.node[tw];
-            __syncwarp();
+#ifdef EGS_RESOLVE_PROF
+            q3_ = clock64() + (ok & 0) + (o_node & 0);
+#endif
+            __syncwarp();                                         // every lane has read the row
             if (lane == 0) {
-              if (ok) { S.rc[tw][g] = cc - rq_c; S.rm[tw][g] = mm - rq_m; }
+              if (ok) { const int v = S.ver[tw]; st_vol(&S.ver[tw], v + 1); S.rc[tw][g] = cc - rq_c; S.rm[tw][g] = mm - rq_m; st_vol(&S.ver[tw], v + 2); }
               S.dirty[tw] = 1;
-              if (from_head) { __threadfence_block(); S.nT = nT + 1; }
+              if (from_head) { __threadfence_block(); st_vol(&S.nT, nT + 1); }
             }
             o_status = ok ? EGS_OK : EGS_ERR_TRANSACT; o_masks = ok ? masks : 0;
           }
-          // ---- release the ticket, then the owner-private part
-          __syncwarp();
-          if (lane == 0) { __threadfence_block(); st_vol(&S.turn, p + 1); }
+          // ---- hand the ticket on (arrive = release), then the owner-private part
+          if (lane == 0) {
+            if (xb != 0) { S.xbest[s] = 0; S.xbest_t[s] = -1; }
+            st_vol(&S.turn, p + 1);
+#if !MW_POLL
+            if (wake >= 0) mbar_arrive(&S.mbar[wake]);
+#endif
+          }
 #ifdef EGS_RESOLVE_PROF
-          { const long long n_ = clock64(); prof[from_head && win != 0 ? 5 : 2] += n_ - tprev; tprev = n_; }
+          { const long long n_ = clock64(); prof[from_head && win != 0 ? 5 : 2] += n_ - tprev;
+            if (!(from_head && win != 0)) { prof[7] += q1_ - tprev; prof[8] += q2_ - q1_; prof[10] += q3_ - q2_; prof[12] += n_ - q3_; }
+            tprev = n_; }
 #endif
           PROF_C(6, 1)
+#if MW_POLL
+          if (lane == 0 && wake >= 0) mbar_arrive(&S.mbar[wake]);   // off the critical path
+#endif
+          const int fit = afit + (bk >= 0);
+          const unsigned long long fd = afd + (bk >= 0 ? ft_u : 0ull);
+          const unsigned long long sd = asd + (bk >= 0 ? score_term_b(sb_u, sc) : 0ull);
           if (lane == 0) {
-            const unsigned ubit = 1u << (u & 31);
             if (u >= 0 && u != tw) {                              // this pod's filter Traded slot u
               if (bk >= 0) { S.st[s][u] = OPT_CACHED; S.al[s][u] = 1u << (bk & 7); S.tkey[s][u] = tradekey; }
               else S.st[s][u] = OPT_UNFIT;
-              S.pmask[s][u >> 5] &= ~ubit;
+              S.pmask[s][u >> 5] &= ~(1u << (u & 31));
             }
-            if (tw >= 0) {                                        // node.go:90-92: the entry is consumed
+            if (win != 0) {                                       // node.go:90-92: the entry is consumed
               S.st[s][tw] = OPT_ABSENT; S.tkey[s][tw] = 0; S.pmask[s][tw >> 5] |= 1u << (tw & 31);
               S.afit[s] = fit - 1; S.afd[s] = fd - S.fterm[tw]; S.asd[s] = sd - score_term_b(S.sbase[tw], key_score(win));
               S.pu[s] = tw;
@@ -923,26 +1039,39 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
             if (a.out.alloc) reinterpret_cast<uint32_t *>(a.out.alloc)[p] = o_masks;
           }
           __syncwarp();
+          if (lmax) {                                             // the columns of the two entries that changed
+            const int seen = S.lm_seen[s];
+            const bool mine = (u >= 0 && u < seen && (u & 31) == lane) || (win != 0 && tw < seen && (tw & 31) == lane);
+            if (__any_sync(0xffffffffu, mine)) {
+              unsigned long long b = 0; int bt = -1;
+#pragma unroll 4
+              for (int t = lane; t < seen; t += 32) { const unsigned long long k = mine ? S.tkey[s][t] : 0ull; if (k > b) { b = k; bt = t; } }
+              if (mine) { lmax[s * 32 + lane] = b; lmax_t[s * 32 + lane] = bt; }
+            }
+            __syncwarp();
+          }
           PROF_T(3)
           continue;
         }
       } else {
-        reason = general_pod(S, a, lk, lane, p, s, ns, D, rke);
+        reason = general_pod(S, a, lk, hpay, lane, p, s, ns);
         PROF_C(9, 1)
       }
-      if (reason) {                                               // the round ends BEFORE pod p
-        if (lane == 0) { S.stop_reason = reason; __threadfence_block(); st_vol(&S.stop, 1); }
+      if (reason) {                                               // the round ends BEFORE pod p: wake every owner
+        if (lane == 0) { S.stop_reason = reason; S.stop_p = p; S.stop = 1; st_vol(&S.turn, p | MW_STOP); }
+        __syncwarp();
+        if (lane < nw && lane != warp) mbar_arrive(&S.mbar[lane]);
         break;
       }
       __syncwarp();
-      if (lane == 0) { __threadfence_block(); st_vol(&S.turn, p + 1); }
+      if (lane == 0) { st_vol(&S.turn, p + 1); if (wake >= 0) mbar_arrive(&S.mbar[wake]); }
       PROF_T(4)
     }
   }
   __syncthreads();
   // ---- epilogue: write the tracked nodes back (each shard its own nodes)
   const int nT = S.nT;
-  const int done = (S.stop ? S.turn : p_end) - p0;
+  const int done = S.stop_p - p0;
   const int nwarps = nthreads >> 5;
   for (int t = warp; t < nT; t += nwarps) {
     const int w = S.node[t];

@@ -194,14 +194,18 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   // ---- resolver geometry
   const int D = h->world;
   int rke = cfg.rkm;
+  auto env_int = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
+  const int use_hpay = cfg.inst != 2 ? env_int("EGS_MW_HPAY", 2) : 0;   // prefetched candidate payload per shape (2: cp.async)
+  const int use_lmax = cfg.inst != 2 ? env_int("EGS_MW_LMAX", 1) : 0;   // cached column maxima of the tracked keys
+  const size_t hp_bytes = (use_hpay ? (size_t)ns_cfg * L.cand_bytes : 0) + (use_lmax ? (size_t)ns_cfg * 32 * 12 : 0);
   {
-    const size_t avail = MW_SMEM_MAX - cfg.smem_struct;
+    const size_t avail = MW_SMEM_MAX - cfg.smem_struct - hp_bytes;
     const size_t per = (size_t)ns_cfg * D * 8;
-    if ((size_t)rke * per > avail) rke = (int)(avail / per);
+    if ((size_t)rke * per > avail) rke = (int)(avail / per) & ~1;   // even: what follows the lists stays 16-byte aligned
     if (rke < 4) return fail(h, EGS_ERR_BAD_ARG, "rounds: shape set too large for the resolver's shared memory");
   }
-  const int nw = std::max(1, std::min(ns_cfg, MW_MAX_WARPS));
-  const size_t smem = cfg.smem_struct + (size_t)ns_cfg * D * rke * 8;
+  const int nw = std::max(1, std::min(ns_cfg, env_int("EGS_MW_WARPS", MW_MAX_WARPS)));
+  const size_t smem = cfg.smem_struct + (size_t)ns_cfg * D * rke * 8 + hp_bytes;
 
   SelectArgs sa; MergeArgs ma; MwArgs ra;
   sa.core = h->d_core; sa.mem = h->d_mem; sa.mem_total = h->d_mem_total;
@@ -212,7 +216,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   ma.out = R.d_bufs + (size_t)h->rank * L.bytes; ma.L = L; ma.ctl = R.d_ctl;
   ra.core = h->d_core; ra.mem = h->d_mem; ra.lo = h->lo; ra.hi = h->hi; ra.policy = h->policy; ra.n_shards = D;
   ra.rd = R.d_rd; ra.tb = tb; ra.obs_pending = R.d_obs; ra.bufs = R.d_bufs; ra.L = L; ra.pod_sidx = R.d_pod_sidx;
-  ra.p0 = -1; ra.p_limit = 0; ra.out = out; ra.ctl = R.d_ctl; ra.rke = rke; ra.nw = nw;
+  ra.p0 = -1; ra.p_limit = 0; ra.out = out; ra.ctl = R.d_ctl; ra.rke = rke; ra.nw = nw; ra.use_hpay = use_hpay; ra.use_lmax = use_lmax;
 
   int ns_round = ns_cfg;                                        // grid of k_merge
   auto launch_round = [&]() -> int {

@@ -58,6 +58,24 @@ class Workload:
                         self.c_off[:n_pods + 1].copy(), self.units[:k].copy())
 
 
+def window(w: "Workload", start: int, n_pods: int) -> "Workload":
+    """Pods [start, start + n_pods) of `w` as a batch of their own (same cluster)."""
+    end = min(start + n_pods, w.n_pods)
+    k0, k1 = int(w.c_off[start]), int(w.c_off[end])
+    return Workload(w.cfg, w.n_nodes, w.gpus, w.mem_total, w.policy, w.core, w.mem,
+                    (w.c_off[start:end + 1] - k0).astype(np.int32), w.units[k0:k1].copy())
+
+
+def shapes_of(w: "Workload"):
+    """Distinct request shapes of the batch, in order of first appearance: tuples of (core, mem, count)."""
+    seen, out = set(), []
+    for p in range(w.n_pods):
+        u = tuple(tuple(int(x) for x in w.units[k]) for k in range(int(w.c_off[p]), int(w.c_off[p + 1])))
+        if u not in seen:
+            seen.add(u); out.append(u)
+    return out
+
+
 def config(cfg: int, n_nodes: int | None = None, n_pods: int | None = None, policy: int | None = None) -> Workload:
     """Config `cfg` of BASELINE.json; n_nodes / n_pods / policy override the named size
     (the generators are prefix-stable, so a smaller size is a prefix of the full one)."""

@@ -116,6 +116,13 @@ int egs_bind(egs_handle *h, int node_id, int n_containers, const egs_unit *units
 int egs_option_peek(egs_handle *h, int node_id, int n_containers, const egs_unit *units,
                     int32_t *out_valid, int32_t *out_score, uint8_t *out_alloc_mask);
 
+/* Bulk form of egs_option_peek: the option cache (node.go:19 `allocated`) of one request on nodes
+ * [node0, node0+n) -- the per-shape part of Status() / a checkpoint.  out_state[i]: 0 no entry, 1 entry
+ * present (possibly stale), 2 no entry and the request is known not to fit the current rows;
+ * out_score[i] / out_alloc_mask[i*EGS_MAX_CONTAINERS + c] are meaningful for state 1.  Any out may be NULL. */
+int egs_option_dump(egs_handle *h, int n_containers, const egs_unit *units, int node0, int n,
+                    uint8_t *out_state, int32_t *out_score, uint8_t *out_alloc_mask);
+
 /* AddPod (scheduler.go:229-245 -> node.go:148-160 with the option rebuilt from the
  * annotations, allocate.go:75-93).  alloc_idx[alloc_off[c] .. alloc_off[c+1]) are the
  * GPU indices of container c in annotation order. */

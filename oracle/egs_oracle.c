@@ -523,6 +523,32 @@ int egso_peek(egso *o, int node, int C, const egso_unit *units, int64_t *score, 
   opt_export(hit, C, alloc_off, alloc_idx);
   return 1;
 }
+/* TEST SUPPORT: install cached options of one request shape on nodes [0, n) (node_ids NULL) -- the state of a
+ * scheduler that already ran: entry i exists when valid[i] != 0, with option.Score = score[i] and
+ * option.Allocated rebuilt from alloc_mask[i][c] (bit g = GPU g of container c; Trade only yields
+ * ascending index lists).  Existing entries of that shape on those nodes are replaced. */
+int egso_cache_load(egso *o, int C, const egso_unit *units, int n, const int32_t *node_ids,
+                    const uint8_t *valid, const int64_t *score, const uint8_t *alloc_mask) {
+  if (C < 1 || C > 4) return ST_BAD_ARG;
+  uint32_t shape = intern(o, C, units);
+  uint32_t key = node_key(o, shape, C, units);
+  for (int i = 0; i < n; i++) {
+    int node = node_ids ? node_ids[i] : i;
+    if (node < 0 || node >= o->nn) return ST_BAD_ARG;
+    node_t *nd = &o->nodes[node];
+    cache_del(nd, key);
+    if (!valid[i]) continue;
+    opt_t op; memset(&op, 0, sizeof op);
+    op.key = key; op.C = C; op.score = score[i];
+    for (int c = 0; c < C; c++) {
+      int k = 0;
+      for (int g = 0; g < 8; g++) if ((alloc_mask[(size_t)i * 4 + c] >> g) & 1) op.idx[c][k++] = (int8_t)g;
+      op.n[c] = (int8_t)k;
+    }
+    cache_put(nd, &op);
+  }
+  return ST_OK;
+}
 /* AddPod scheduler.go:229-245 */
 int egso_add_pod(egso *o, int node, int C, const egso_unit *units, const int32_t *alloc_off,
                  const int32_t *alloc_idx, uint64_t uid) {

@@ -56,6 +56,7 @@ def lib():
         L.egso_peek.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.egso_add_pod.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.egso_forget_pod.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.egso_cache_load.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.egso_known_pod.argtypes = [C.c_void_p, C.c_uint64]
         L.egso_released_pod.argtypes = [C.c_void_p, C.c_uint64]
         L.egso_schedule_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + \
@@ -171,6 +172,13 @@ class OracleC:
     def forget_pod(self, node: int, req, alloc, uid: int) -> int:
         off, idx = _alloc_arrays(alloc)
         return self.L.egso_forget_pod(self.h, node, len(req), _units(req), _ptr(off), _ptr(idx), uid)
+
+    def cache_load(self, req, valid, score, alloc_mask) -> int:
+        """Install cached options of shape `req` on nodes 0..n-1 (state of a scheduler that already ran)."""
+        v = np.ascontiguousarray(valid, dtype=np.uint8)
+        sc = np.ascontiguousarray(score, dtype=np.int64)
+        am = np.ascontiguousarray(alloc_mask, dtype=np.uint8)
+        return self.L.egso_cache_load(self.h, len(req), _units(req), len(v), None, _ptr(v), _ptr(sc), _ptr(am))
 
     def known_pod(self, uid: int) -> bool:
         return bool(self.L.egso_known_pod(self.h, uid))

@@ -107,6 +107,66 @@ def test_cfg4_prefix(mode):
     _compare_batch(_egs().workloads.config(4, n_pods=3000), mode, threads=4)
 
 
+def _late_window(cfg, policy, K, W, threads=4, sample=4000):
+    """The GPU engine schedules the first K pods; rows and every option cache are dumped through the ABI and
+    loaded into a FRESH oracle (egso_cache_load); both then schedule pods [K, K+W) and must agree on all six
+    outputs, the final rows and the final caches.  This puts the oracle into the late, full-cluster regime
+    (stale options, bind failures, unfit nodes) that a prefix from an empty cluster never reaches."""
+    eg = _egs()
+    full = eg.workloads.config(cfg, n_pods=K + W, policy=policy)
+    e = _gpu_for(full)
+    pre = full.prefix(K)
+    e.schedule_batch(pre.c_off, pre.units, mode=2)
+    core, mem, _, _ = e.state_dump()
+    o = oc.OracleC(full.policy)
+    for n in range(full.n_nodes):
+        o.add_node(100 * full.gpus, full.mem_total * full.gpus)
+        o.set_rows(n, core[n, :full.gpus], mem[n, :full.gpus])
+    shapes = eg.workloads.shapes_of(full)
+    n_cached = 0
+    for sh in shapes:
+        st, sc, am = e.option_dump(list(sh))
+        assert o.cache_load(list(sh), st == 1, sc, am) == 0
+        n_cached += int((st == 1).sum())
+    assert n_cached > 0
+    win = eg.workloads.window(full, K, W)
+    ref = o.schedule_batch(win.c_off, win.units64(), threads=threads)
+    got = e.schedule_batch(win.c_off, win.units, mode=2)
+    for f in FIELDS:
+        assert np.array_equal(ref[f], got[f]), f"cfg{cfg} K={K}: {f} differs at pod {np.argwhere(ref[f] != got[f])[:3]}"
+    core, mem, _, _ = e.state_dump()
+    rng = np.random.default_rng(K)
+    nodes = set(int(x) for x in rng.integers(0, full.n_nodes, sample)) | set(int(x) for x in ref["node"] if x >= 0)
+    dumps = {sh: e.option_dump(list(sh)) for sh in shapes}
+    for n in nodes:
+        rows = o.rows(n)
+        assert [int(x) for x in core[n, :full.gpus]] == [r[0] for r in rows]
+        assert [int(x) for x in mem[n, :full.gpus]] == [r[1] for r in rows]
+        for sh in shapes:
+            st, sc, am = dumps[sh]
+            pk = o.peek(n, list(sh))
+            assert (pk is not None) == (st[n] == 1), f"cache presence differs node {n} shape {sh}"
+            if pk is not None:
+                assert pk[1] == int(sc[n]) and pk[0] == [[g for g in range(8) if am[n, c] >> g & 1] for c in range(len(sh))]
+    return ref
+
+
+@pytest.mark.parametrize("K", [250_000, 500_000, 750_000, 900_000, 990_000])
+def test_cfg4_late_windows(K):
+    """config 4 at full size, 3000-pod windows deep inside the 1M-pod batch (incl. the > 80 % regime)."""
+    _late_window(4, None, K, 3000)
+
+
+@pytest.mark.parametrize("K", [100_000, 400_000])
+def test_cfg3_late_windows(K):
+    _late_window(3, None, K, 1500)
+
+
+@pytest.mark.parametrize("K", [50_000, 90_000])
+def test_cfg2_late_windows(K):
+    _late_window(2, None, K, 5000)
+
+
 def test_pressure_small_cluster():
     """Few nodes, many pods: nodes fill up, unfit nodes and stale-option bind failures appear."""
     eg = _egs()
