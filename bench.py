@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--roofline-only", action="store_true", help="PROFILING ONLY: just the 4M-node k_evaluate leg (for ncu)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the side measurements of BASELINE configs 1-3")
     return ap.parse_args()
 
 
@@ -176,6 +177,95 @@ def workload_config(w, args, extra=None):
     return c
 
 
+FIELDS = ("node", "status", "alloc_mask", "fit_count", "fit_digest", "score_digest")
+
+
+def out_hash(out) -> str:
+    """sha256 over the six per-pod output arrays of a batch."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in FIELDS:
+        h.update(np.ascontiguousarray(out[f]).tobytes())
+    return h.hexdigest()
+
+
+def sharded_handle(eg, w, rank, world, local, dist, sub=None):
+    """Handle on this rank's node range of a `sub`-rank shard group (ranks >= sub take no part)."""
+    sub = world if sub is None else sub
+    cap = eg.capi
+    box = [cap.comm_unique_id() if (rank == 0 and sub > 1) else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    if rank >= sub:
+        return None
+    e = eg.Egs(w.policy, w.n_nodes, 8, local)
+    if sub > 1:
+        e.shard_set(rank, sub)
+        e.comm_init(box[0])
+    e.state_load_bulk(0, w.gpus, w.mem_total, w.core, w.mem)
+    return e
+
+
+def extra_config(eg, cfg, rank, world, local, dist, torch, steps, oracle_pods):
+    """One of the other BASELINE configs: decisions/s of the whole batch (device-synchronised host clock) + parity:
+    sharded == unsharded outputs, rounds engine == one-pass-per-pod engine (when affordable), and the oracle as
+    CHECKER on a pod prefix."""
+    w = eg.workloads.config(cfg)
+    sub = 1 if cfg in (1, 2) else min(world, 4)
+    e = sharded_handle(eg, w, rank, world, local, dist, sub)
+    line = None
+    hashes = [None]
+    if e is not None:
+        e.snapshot()
+        e.schedule_batch(w.c_off, w.units)                       # warm-up (also compiles nothing: no JIT anywhere)
+        dev = torch.device("cuda", local)
+        P = w.n_pods
+        keep = [torch.empty(P, dtype=torch.int32, device=dev), torch.empty(P, dtype=torch.int32, device=dev),
+                torch.empty((P, 4), dtype=torch.uint8, device=dev), torch.empty(P, dtype=torch.int32, device=dev),
+                torch.empty(P, dtype=torch.int64, device=dev), torch.empty(P, dtype=torch.int64, device=dev)]
+        dptrs = [t.data_ptr() for t in keep]                      # all six per-pod outputs are written, as in the headline
+        ms = []
+        for _ in range(steps):
+            e.restore()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            e.schedule_batch_device(w.c_off, w.units, dptrs)
+            torch.cuda.synchronize()
+            ms.append((time.perf_counter() - t0) * 1e3)
+        e.restore()
+        out = e.schedule_batch(w.c_off, w.units)
+        hashes = [out_hash(out)]
+    if world > 1:
+        allh = [None] * world
+        dist.all_gather_object(allh, hashes[0])
+    else:
+        allh = hashes
+    if rank == 0:
+        ms_step = float(np.median(ms))
+        par = {"ranks": sub, "ranks_equal": len({h for h in allh[:sub]}) == 1}
+        if sub > 1:                                               # the same batch on ONE unsharded handle
+            e1 = eg.Egs(w.policy, w.n_nodes, 8, local)
+            e1.state_load_bulk(0, w.gpus, w.mem_total, w.core, w.mem)
+            par["equals_unsharded"] = out_hash(e1.schedule_batch(w.c_off, w.units)) == allh[0]
+            e1.close()
+        if cfg in (1, 2):                                         # independent engine: one full pass per pod
+            e2 = eg.Egs(w.policy, w.n_nodes, 8, local)
+            e2.state_load_bulk(0, w.gpus, w.mem_total, w.core, w.mem)
+            par["equals_rescan_engine"] = out_hash(e2.schedule_batch(w.c_off, w.units, mode=eg.capi.EGS_MODE_RESCAN)) == allh[0]
+            e2.close()
+        if oracle_pods:                                           # the oracle as checker, bounded prefix
+            k = min(oracle_pods, w.n_pods)
+            ref = oracle_for(w).schedule_batch(w.c_off[:k + 1], w.units64()[:int(w.c_off[k])], threads=4)
+            par["oracle_prefix_pods"] = k
+            par["equals_oracle_on_prefix"] = all(np.array_equal(ref[f], out[f][:k]) for f in FIELDS)
+        line = {"workload": eg.workloads.CONFIG_NAMES[cfg], "n_gpus": sub, "value": w.n_pods / (ms_step * 1e-3),
+                "unit": "decisions/s", "ms_per_step": ms_step, "steps": steps, "policy": eg.workloads.POLICY_NAMES[w.policy],
+                "timing": "host clock around a device-synchronised resident step", "parity": par}
+    if e is not None:
+        e.close()
+    return line
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -296,10 +386,38 @@ def main():
                      "rounds": st1["rounds"] - st0["rounds"], "tracked_nodes": st1["tracked"] - st0["tracked"],
                      "stops": {k: st1[k] - st0[k] for k in ("stop_limit", "stop_shape", "stop_tracked_full", "stop_list_dry")},
                      "note": "device time per kernel of one untimed step (events between launches, includes gaps); "
-                             "k_resolve is one warp bound by dependent-instruction latency, not by memory"}
+                             "k_resolve_mw is one CTA (one owner warp per request shape) bound by dependent-instruction latency, not by memory"}
         e.profile_reset(False)
     except Exception as ex:  # never let instrumentation break the bench line
         breakdown = {"error": repr(ex)}
+
+    # ---- driver-visible parity of the sharded run: every rank's outputs identical, and identical to ONE unsharded
+    # handle scheduling the same batch (SURVEY 8e "outputs identical")
+    parity = None
+    if world > 1:
+        e.restore()
+        mine = out_hash(e.schedule_batch(w.c_off, w.units, mode=mode))
+        allh = [None] * world
+        dist.all_gather_object(allh, mine)
+        if rank == 0:
+            e1 = egs_b200.Egs(w.policy, w.n_nodes, 8, local)
+            e1.state_load_bulk(0, w.gpus, w.mem_total, w.core, w.mem)
+            un = out_hash(e1.schedule_batch(w.c_off, w.units, mode=mode))
+            e1.close()
+            parity = {"ranks": world, "ranks_equal": len(set(allh)) == 1, "equals_unsharded": un == allh[0],
+                      "what": "sha256 over node/status/alloc/fit_count/fit_digest/score_digest of all pods"}
+
+    # ---- the other BASELINE configs (1, 2 on one GPU; 3 on min(world, 4) GPUs)
+    configs = []
+    if not args.pods and not args.no_configs and args.cfg == 4:
+        for cfg, opods in ((1, 10000), (2, 3000), (3, 300)):
+            try:
+                line_c = extra_config(egs_b200, cfg, rank, world, local, dist if world > 1 else None, torch, 2,
+                                      0 if args.no_cpu else opods)
+            except Exception as ex:  # never let a side measurement break the bench line
+                line_c = {"workload": egs_b200.workloads.CONFIG_NAMES[cfg], "error": repr(ex)} if rank == 0 else None
+            if rank == 0:
+                configs.append(line_c)
 
     if rank != 0:
         if world > 1:
@@ -360,7 +478,7 @@ def main():
             "l2": "256 MB buffer written between timed steps (L2 flush); within a step the 6.4 MB state is "
                   "L2-resident by construction"}),
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-        "step_breakdown": breakdown,
+        "step_breakdown": breakdown, "parity_checked": parity, "configs": configs,
     }
     if args.pods:
         line["profiling_subset"] = True

@@ -372,7 +372,7 @@ static int load_rows(egs_handle *h, int node0, int n, int gpu_count, int mem_tot
 
 // podsMap entries of nodes [node0, node0+n) vanish with their NodeAllocator (one pass)
 static void drop_node_pods(egs_handle *h, int node0, int n) {
-  if (h->pods_map.empty()) return;
+  if (h->pods_map.empty() && h->auto_batches.empty()) return;   // batches with library-assigned uids live in auto_batches
   if (node0 == 0 && n >= h->max_nodes) {
     h->pods_map.clear();
     // auto batches: every node reloaded -> no podsMap entry survives; podMaps (scheduler level) does

@@ -92,6 +92,18 @@ struct P {
   void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
   bool fail(const char *m) { if (err.empty()) err = m; return false; }
   bool lit(const char *s) { size_t n = strlen(s); if ((size_t)(e - p) < n || memcmp(p, s, n)) return false; p += n; return true; }
+  int depth = 0;                                              // nesting of the value being read (encoding/json caps it at 10000)
+  bool enter() { if (++depth > 10000) return fail("exceeded max depth"); return true; }
+  bool hex4(unsigned *cp) {
+    if (e - p < 4) return false;
+    unsigned v = 0;
+    for (int k = 0; k < 4; k++) {
+      const char h = *p++;
+      if (h >= '0' && h <= '9') v = v * 16 + (h - '0'); else if ((h | 32) >= 'a' && (h | 32) <= 'f') v = v * 16 + ((h | 32) - 'a' + 10); else return false;
+    }
+    *cp = v;
+    return true;
+  }
   bool str(std::string *out) {                                // out may be null (skip)
     ws();
     if (p >= e || *p != '"') return fail("string expected");
@@ -101,11 +113,16 @@ struct P {
         if (++p >= e) return fail("bad escape");
         char c = *p++;
         if (c == 'u') {
-          if (e - p < 4) return fail("bad \\u");
           unsigned cp = 0;
-          for (int k = 0; k < 4; k++) { char h = *p++; cp = cp * 16 + (h <= '9' ? h - '0' : (h | 32) - 'a' + 10); }
+          if (!hex4(&cp)) return fail("invalid character in \\u hexadecimal character escape");
+          if (cp >= 0xD800 && cp < 0xDC00) {                      // high surrogate: needs \uDC00..\uDFFF right after
+            unsigned lo = 0; const char *save = p;
+            if (e - p >= 6 && p[0] == '\\' && p[1] == 'u' && (p += 2, hex4(&lo)) && lo >= 0xDC00 && lo < 0xE000) cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+            else { p = save; cp = 0xFFFD; }                       // encoding/json: unpaired surrogate -> U+FFFD
+          } else if (cp >= 0xDC00 && cp < 0xE000) cp = 0xFFFD;
           if (out) { if (cp < 0x80) out->push_back((char)cp); else if (cp < 0x800) { out->push_back((char)(0xC0 | cp >> 6)); out->push_back((char)(0x80 | (cp & 63))); }
-                     else { out->push_back((char)(0xE0 | cp >> 12)); out->push_back((char)(0x80 | ((cp >> 6) & 63))); out->push_back((char)(0x80 | (cp & 63))); } }
+                     else if (cp < 0x10000) { out->push_back((char)(0xE0 | cp >> 12)); out->push_back((char)(0x80 | ((cp >> 6) & 63))); out->push_back((char)(0x80 | (cp & 63))); }
+                     else { out->push_back((char)(0xF0 | cp >> 18)); out->push_back((char)(0x80 | ((cp >> 12) & 63))); out->push_back((char)(0x80 | ((cp >> 6) & 63))); out->push_back((char)(0x80 | (cp & 63))); } }
         } else if (out) {
           out->push_back(c == 'n' ? '\n' : c == 't' ? '\t' : c == 'r' ? '\r' : c == 'b' ? '\b' : c == 'f' ? '\f' : c);
         }
@@ -122,14 +139,15 @@ struct P {
     if (*p == '{' || *p == '[') {
       const char close = *p == '{' ? '}' : ']';
       const bool obj = *p == '{';
+      if (!enter()) return false;
       p++; ws();
-      if (p < e && *p == close) { p++; return true; }
+      if (p < e && *p == close) { p++; depth--; return true; }
       for (;;) {
         if (obj) { if (!str(nullptr)) return false; ws(); if (p >= e || *p++ != ':') return fail("':' expected"); }
         if (!skip()) return false;
         ws();
         if (p < e && *p == ',') { p++; continue; }
-        if (p < e && *p == close) { p++; return true; }
+        if (p < e && *p == close) { p++; depth--; return true; }
         return fail("',' expected");
       }
     }
@@ -141,8 +159,9 @@ struct P {
     ws();
     if (lit("null")) return true;
     if (p >= e || *p != '{') return fail("object expected");
+    if (!enter()) return false;
     p++; ws();
-    if (p < e && *p == '}') { p++; return true; }
+    if (p < e && *p == '}') { p++; depth--; return true; }
     for (;;) {
       std::string key;
       if (!str(&key)) return false;
@@ -151,7 +170,7 @@ struct P {
       if (!f(key)) return false;
       ws();
       if (p < e && *p == ',') { p++; continue; }
-      if (p < e && *p == '}') { p++; return true; }
+      if (p < e && *p == '}') { p++; depth--; return true; }
       return fail("',' or '}' expected");
     }
   }
@@ -159,13 +178,14 @@ struct P {
     ws();
     if (lit("null")) return true;
     if (p >= e || *p != '[') return fail("array expected");
+    if (!enter()) return false;
     p++; ws();
-    if (p < e && *p == ']') { p++; return true; }
+    if (p < e && *p == ']') { p++; depth--; return true; }
     for (;;) {
       if (!f()) return false;
       ws();
       if (p < e && *p == ',') { p++; continue; }
-      if (p < e && *p == ']') { p++; return true; }
+      if (p < e && *p == ']') { p++; depth--; return true; }
       return fail("',' or ']' expected");
     }
   }
@@ -282,21 +302,28 @@ void AppendJsonString(std::string *out, std::string_view s) {   // encoding/json
 }
 
 std::string EncodeFilterResult(const std::vector<std::string> &node_names, const std::map<std::string, std::string> &failed,
-                               const std::string &error) {
-  // ExtenderFilterResult{Nodes omitempty (nil), NodeNames *[]string omitempty (non-nil pointer: always present),
-  //                      FailedNodes omitempty, Error omitempty}; predicate.go:33-37 sets NodeNames = &filterdNodes
+                               const std::string &error, bool has_node_names) {
+  // ExtenderFilterResult{Nodes omitempty (nil), NodeNames *[]string omitempty, FailedNodes omitempty, Error omitempty}.
+  // predicate.go:33-37 sets NodeNames = &filterdNodes (a non-nil pointer: present even when empty); every error
+  // path (predicate.go:21-31, routes.go:51-64) leaves NodeNames nil: the member is omitted.
   std::string o;
   o.reserve(32 + node_names.size() * 16);
-  o += "{\"nodenames\":[";
-  for (size_t i = 0; i < node_names.size(); i++) { if (i) o.push_back(','); AppendJsonString(&o, node_names[i]); }
-  o += "]";
+  o += "{";
+  bool any = false;
+  if (has_node_names) {
+    o += "\"nodenames\":[";
+    for (size_t i = 0; i < node_names.size(); i++) { if (i) o.push_back(','); AppendJsonString(&o, node_names[i]); }
+    o += "]";
+    any = true;
+  }
   if (!failed.empty()) {
-    o += ",\"failedNodes\":{";
+    o += any ? ",\"failedNodes\":{" : "\"failedNodes\":{";
+    any = true;
     bool first = true;
     for (const auto &kv : failed) { if (!first) o.push_back(','); first = false; AppendJsonString(&o, kv.first); o.push_back(':'); AppendJsonString(&o, kv.second); }
     o += "}";
   }
-  if (!error.empty()) { o += ",\"error\":"; AppendJsonString(&o, error); }
+  if (!error.empty()) { o += any ? ",\"error\":" : "\"error\":"; AppendJsonString(&o, error); }
   o += "}";
   return o;
 }

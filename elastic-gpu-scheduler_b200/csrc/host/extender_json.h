@@ -51,8 +51,9 @@ bool ParseQuantityValue(std::string_view q, int64_t *out);
 std::string ParseExtenderArgs(std::string_view json, NodeInterner *nodes, ExtenderArgs *out);
 std::string ParseBindingArgs(std::string_view json, BindingArgs *out);
 
+// has_node_names == false: NodeNames is a nil pointer (every error path) and the member is omitted
 std::string EncodeFilterResult(const std::vector<std::string> &node_names, const std::map<std::string, std::string> &failed,
-                               const std::string &error);
+                               const std::string &error, bool has_node_names = true);
 std::string EncodeHostPriorityList(const std::vector<std::pair<std::string, int64_t>> &scores);
 std::string EncodeBindingResult(const std::string &error);
 void AppendJsonString(std::string *out, std::string_view s);   // Go encoding/json string escaping

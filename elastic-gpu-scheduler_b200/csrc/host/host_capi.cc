@@ -29,7 +29,7 @@ void *egsh_create(int policy, int max_nodes, int device) {
   if (!c->sch->ok()) { delete c->sch; delete c; return nullptr; }
   return c;
 }
-void egsh_destroy(void *h) { HostCtx *c = (HostCtx *)h; delete c->sch; delete c; }
+void egsh_destroy(void *h) { if (!h) return; HostCtx *c = (HostCtx *)h; delete c->sch; delete c; }
 void egsh_register_node(void *h, const char *name, int64_t core_alloc, int64_t mem_alloc) {
   NodeInfo &n = ((HostCtx *)h)->cluster[name];
   n.core_allocatable = core_alloc; n.mem_allocatable = mem_alloc;
@@ -90,6 +90,78 @@ const char *egsh_status(void *h) { return ret((HostCtx *)h, ((HostCtx *)h)->sch-
 
 struct JsonCtx { NodeInterner nodes; ExtenderArgs args; BindingArgs bind; std::string buf; };
 
+// ---- the three extender routes end to end: HTTP body -> JSON decode -> plugin verb (libegs on the GPU) -> JSON body.
+// pkg/routes/routes.go:39-163 over pkg/server/{predicate,priority,bind}.go.  *http_status receives 200 / 500;
+// a request the reference answers by panicking (routes.go:98-109) yields status -1 and the panic text.
+struct RouteCtx {
+  HostCtx *host;
+  NodeInterner nodes;                                  // per-process interning of the request's node names
+  std::map<std::string, Pod> pods;                     // the "apiserver": ns/name -> pod (GetPod of bind.go:36)
+  std::string buf;
+};
+static const char kNotCacheCapable[] = "elastic-gpu-scheduler extender must be configured with nodeCacheCapable=true";
+
+extern "C" {
+void *egsr_new(void *host) { RouteCtx *r = new RouteCtx(); r->host = (HostCtx *)host; return r; }
+void egsr_free(void *r) { delete (RouteCtx *)r; }
+void egsr_register_pod(void *r, void *pod) { Pod *p = (Pod *)pod; ((RouteCtx *)r)->pods[p->ns + "/" + p->name] = *p; }
+
+// POST /scheduler/filter
+const char *egsr_filter(void *rc, const char *json, int64_t len, int *http_status) {
+  RouteCtx *r = (RouteCtx *)rc;
+  *http_status = 200;
+  ExtenderArgs a;
+  std::string err = ParseExtenderArgs(std::string_view(json, (size_t)len), &r->nodes, &a);
+  if (!err.empty()) { r->buf = EncodeFilterResult({}, {}, err, false); return r->buf.c_str(); }                 // routes.go:51-58
+  if (!a.has_nodenames) { r->buf = EncodeFilterResult({}, {}, kNotCacheCapable, false); return r->buf.c_str(); } // routes.go:59-64
+  if (!CudaUnitScheduler::Handles(a.pod)) {                                                                     // predicate.go:19-24
+    r->buf = EncodeFilterResult({}, {}, "cannot find scheduler for pod " + a.pod.ns + "/" + a.pod.name, false);
+    return r->buf.c_str();
+  }
+  std::vector<std::string> names; names.reserve(a.node_ids.size());
+  for (int32_t id : a.node_ids) names.push_back(r->nodes.Name(id));
+  std::vector<std::string> filtered; std::map<std::string, std::string> failed;
+  err = r->host->sch->Assume(names, a.pod, &filtered, &failed);
+  if (!err.empty()) { r->buf = EncodeFilterResult({}, {}, err, false); return r->buf.c_str(); }                 // predicate.go:27-31
+  r->buf = EncodeFilterResult(filtered, failed, "", true);
+  return r->buf.c_str();
+}
+
+// POST /scheduler/priorities
+const char *egsr_priorities(void *rc, const char *json, int64_t len, int *http_status) {
+  RouteCtx *r = (RouteCtx *)rc;
+  *http_status = 200;
+  ExtenderArgs a;
+  std::string err = ParseExtenderArgs(std::string_view(json, (size_t)len), &r->nodes, &a);
+  if (!err.empty()) { *http_status = -1; r->buf = "panic: " + err; return r->buf.c_str(); }                     // routes.go:98-100
+  if (!a.has_nodenames) { *http_status = -1; r->buf = "panic: runtime error: invalid memory address or nil pointer dereference"; return r->buf.c_str(); }   // priority.go:19
+  if (!CudaUnitScheduler::Handles(a.pod)) { *http_status = -1; r->buf = "panic: cannot find scheduler for pod " + a.pod.ns + "/" + a.pod.name; return r->buf.c_str(); }
+  std::vector<std::string> names; names.reserve(a.node_ids.size());
+  for (int32_t id : a.node_ids) names.push_back(r->nodes.Name(id));
+  std::vector<int64_t> scores = r->host->sch->Score(names, a.pod);
+  std::vector<std::pair<std::string, int64_t>> list; list.reserve(names.size());
+  for (size_t i = 0; i < names.size(); i++) list.emplace_back(names[i], scores[i]);
+  r->buf = EncodeHostPriorityList(list);
+  return r->buf.c_str();
+}
+
+// POST /scheduler/bind
+const char *egsr_bind(void *rc, const char *json, int64_t len, int *http_status) {
+  RouteCtx *r = (RouteCtx *)rc;
+  BindingArgs b;
+  std::string err = ParseBindingArgs(std::string_view(json, (size_t)len), &b);
+  if (err.empty()) {
+    auto it = r->pods.find(b.pod_namespace + "/" + b.pod_name);
+    if (it == r->pods.end()) err = "pods \"" + b.pod_name + "\" not found";                                    // GetPod, pod.go:110-126
+    else if (!CudaUnitScheduler::Handles(it->second)) err = "cannot find scheduler for pod " + b.pod_namespace + "/" + b.pod_name;
+    else err = r->host->sch->Bind(b.node, &it->second);
+  }
+  *http_status = err.empty() ? 200 : 500;                                                                       // routes.go:146-158
+  r->buf = EncodeBindingResult(err);
+  return r->buf.c_str();
+}
+}
+
 extern "C" {
 void *egsj_new() { return new JsonCtx(); }
 void egsj_free(void *c) { delete (JsonCtx *)c; }
@@ -133,6 +205,12 @@ const char *egsj_encode_filter(void *c, const char *names, const char *failed, c
   split(names, [&](const std::string &l) { nn.push_back(l); });
   split(failed, [&](const std::string &l) { size_t t = l.find('\t'); ff[l.substr(0, t)] = t == std::string::npos ? "" : l.substr(t + 1); });
   j->buf = EncodeFilterResult(nn, ff, error);
+  return j->buf.c_str();
+}
+// an error path of the filter verb: NodeNames stays nil (predicate.go:21-31, routes.go:51-64)
+const char *egsj_encode_filter_error(void *c, const char *error) {
+  JsonCtx *j = (JsonCtx *)c;
+  j->buf = EncodeFilterResult({}, {}, error, false);
   return j->buf.c_str();
 }
 const char *egsj_encode_priorities(void *c, const char *names, const int64_t *scores, int n) {

@@ -33,6 +33,11 @@ def _load():
             getattr(L, f).restype = cp; getattr(L, f).argtypes = [vp, vp]
         L.egsh_known_pod.argtypes = [vp, vp]; L.egsh_released_pod.argtypes = [vp, vp]
         L.egsh_status.restype = cp; L.egsh_status.argtypes = [vp]
+        L.egsr_new.restype = vp; L.egsr_new.argtypes = [vp]
+        L.egsr_free.argtypes = [vp]
+        L.egsr_register_pod.argtypes = [vp, vp]
+        for f in ("egsr_filter", "egsr_priorities", "egsr_bind"):
+            getattr(L, f).restype = cp; getattr(L, f).argtypes = [vp, cp, i64, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -53,7 +58,9 @@ class Pod:
 
     def __del__(self):
         try:
-            self.L.egsh_pod_free(self.p)
+            if getattr(self, "p", None):
+                self.L.egsh_pod_free(self.p)
+                self.p = None
         except Exception:
             pass
 
@@ -67,7 +74,9 @@ class CudaUnitScheduler:
 
     def __del__(self):
         try:
-            self.L.egsh_destroy(self.h)
+            if getattr(self, "h", None):
+                self.L.egsh_destroy(self.h)
+                self.h = None
         except Exception:
             pass
 
@@ -128,3 +137,38 @@ class CudaUnitScheduler:
             k, a, b = line.split("\t")
             (ann if k == "A" else lab)[a] = b
         return ann, lab
+
+
+class ExtenderRoutes:
+    """The three extender routes end to end over a CudaUnitScheduler: HTTP body in, (status, body) out
+    (pkg/routes/routes.go:39-163).  status -1: the reference would panic (body = the panic text)."""
+
+    def __init__(self, sched: CudaUnitScheduler):
+        self.L = _load()
+        self.s = sched
+        self.r = self.L.egsr_new(sched.h)
+
+    def __del__(self):
+        try:
+            if getattr(self, "r", None):
+                self.L.egsr_free(self.r)
+                self.r = None
+        except Exception:
+            pass
+
+    def register_pod(self, pod: Pod):
+        self.L.egsr_register_pod(self.r, pod.p)
+
+    def _call(self, f, body: bytes):
+        st = C.c_int(0)
+        out = f(self.r, body, len(body), C.byref(st))
+        return st.value, out.decode()
+
+    def filter(self, body: bytes):
+        return self._call(self.L.egsr_filter, body)
+
+    def priorities(self, body: bytes):
+        return self._call(self.L.egsr_priorities, body)
+
+    def bind(self, body: bytes):
+        return self._call(self.L.egsr_bind, body)

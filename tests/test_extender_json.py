@@ -13,7 +13,7 @@ def J():
     L = C.CDLL(egs_b200._build.build_host())
     L.egsj_new.restype = C.c_void_p
     for f in ("egsj_parse_args", "egsj_pod_dump", "egsj_parse_binding", "egsj_encode_filter", "egsj_encode_priorities",
-              "egsj_encode_binding", "egsj_node_name"):
+              "egsj_encode_binding", "egsj_node_name", "egsj_encode_filter_error"):
         getattr(L, f).restype = C.c_char_p
     L.egsj_parse_args.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     L.egsj_parse_binding.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
@@ -24,6 +24,7 @@ def J():
     L.egsj_node_name.argtypes = [C.c_void_p, C.c_int]
     L.egsj_quantity.argtypes = [C.c_char_p, C.POINTER(C.c_int64)]
     L.egsj_encode_filter.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p]
+    L.egsj_encode_filter_error.argtypes = [C.c_void_p, C.c_char_p]
     L.egsj_encode_priorities.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
     L.egsj_encode_binding.argtypes = [C.c_void_p, C.c_char_p]
     L.egsj_free.argtypes = [C.c_void_p]
@@ -106,4 +107,32 @@ def test_large_filter_request_throughput(J):
         assert J.egsj_parse_args(ctx, body, len(body)) == b""
     dt = (time.perf_counter() - t) / 5
     assert J.egsj_n_nodes(ctx) == 100000 and dt < 0.5, dt
+    J.egsj_free(ctx)
+
+
+def test_filter_error_paths_omit_nodenames(J):
+    """predicate.go:21-31 / routes.go:51-64 return ExtenderFilterResult{Error: ...} with a nil NodeNames pointer:
+    encoding/json omits the member; the normal path keeps "nodenames":[] even when nothing fits."""
+    ctx = J.egsj_new()
+    msg = "elastic-gpu-scheduler extender must be configured with nodeCacheCapable=true"
+    assert J.egsj_encode_filter_error(ctx, msg.encode()) == json.dumps({"error": msg}, separators=(",", ":")).encode()
+    assert J.egsj_encode_filter(ctx, b"", b"n1\tno enough resource to allocate", b"") == \
+        b'{"nodenames":[],"failedNodes":{"n1":"no enough resource to allocate"}}'
+    J.egsj_free(ctx)
+
+
+def test_parser_hardening(J):
+    ctx = J.egsj_new()
+    deep = b'{"pod":{"metadata":{"x":' + b"[" * 20000 + b"]" * 20000 + b'}},"nodenames":[]}'
+    assert b"max depth" in J.egsj_parse_args(ctx, deep, len(deep))                  # encoding/json: "exceeded max depth"
+    ok = b'{"pod":{"metadata":{"x":' + b"[" * 500 + b"]" * 500 + b',"name":"p"}},"nodenames":["a"]}'
+    assert J.egsj_parse_args(ctx, ok, len(ok)) == b""
+    bad = b'{"pod":{"metadata":{"name":"a\\u12G4"}},"nodenames":[]}'
+    assert J.egsj_parse_args(ctx, bad, len(bad)) != b""                             # non-hex digit in \\u escape
+    pair = json.dumps({"pod": {"metadata": {"name": "p", "annotations": {"k": "\U0001F600 ok"}}}, "nodenames": []}).encode()
+    assert b"\\ud83d\\ude00" in pair                                              # json.dumps emits a surrogate pair
+    assert J.egsj_parse_args(ctx, pair, len(pair)) == b""
+    assert "\U0001F600 ok".encode() in J.egsj_pod_dump(ctx)
+    lone = b'{"pod":{"metadata":{"name":"p","annotations":{"k":"\\ud83d!"}}},"nodenames":[]}'
+    assert J.egsj_parse_args(ctx, lone, len(lone)) == b"" and "\ufffd!".encode() in J.egsj_pod_dump(ctx)
     J.egsj_free(ctx)

@@ -110,3 +110,24 @@ def test_mode_switching_keeps_state_consistent():
         req = [tuple(int(x) for x in w.units[w.c_off[hi - 1]])]
         assert list(e.filter(None, req)) == list(o.filter(None, req))          # verbs see the tables the batch left
         assert list(e.score(None, req)[1]) == [int(x) for x in o.score(None, req)[1]]
+
+
+def test_node_reload_after_auto_uid_batch_drops_pods_map():
+    """A batch with library-assigned uids keeps podsMap membership in the batch's result arrays; reloading the node
+    (a fresh NodeAllocator, node.go:42-50) must drop it all the same: a later ForgetPod of such a uid is a no-op on
+    the rows (node.go:131) and a bind with that uid transacts again (node.go:149)."""
+    eg = _eg()
+    e = eg.Egs(0, 1)
+    e.node_set_allocatable(0, 200, 32)
+    c_off = np.array([0, 1], np.int32)
+    units = np.array([[20, 4, 0]], np.int32)
+    out = e.schedule_batch(c_off, units, mode=2)                                # uids == NULL: library-assigned
+    assert out["status"][0] == 0 and out["node"][0] == 0
+    uid = 0x8000000000000000
+    assert e.pod_known(uid)
+    g = int(np.log2(out["alloc_mask"][0][0]))
+    assert e.node_set(0, 2, 16) == 0                                            # node reloaded: rows full again
+    assert e.rows(0) == [(100, 16), (100, 16)]
+    assert e.pod_cancel(0, [(20, 4, 0)], [[g]], uid) == 0                       # not in the node's podsMap any more
+    assert e.rows(0) == [(100, 16), (100, 16)]                                  # -> Cancel must not run
+    assert e.pod_released(uid)                                                  # scheduler-level podMaps had it
