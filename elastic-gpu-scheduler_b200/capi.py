@@ -25,7 +25,7 @@ SYMBOLS = [
     "egs_node_set_allocatable", "egs_node_set", "egs_state_load", "egs_state_load_bulk", "egs_state_dump",
     "egs_state_snapshot", "egs_state_restore",
     "egs_filter", "egs_score", "egs_bind", "egs_option_peek", "egs_option_dump", "egs_pod_apply", "egs_node_replay_pod", "egs_pod_cancel",
-    "egs_pod_known", "egs_pod_released", "egs_schedule_batch", "egs_schedule_batch_device",
+    "egs_pod_known", "egs_pod_released", "egs_schedule_batch", "egs_schedule_batch_vec", "egs_schedule_batch_device",
     "egs_shard_set", "egs_shard_range", "egs_comm_unique_id", "egs_comm_init", "egs_profile_evaluate", "egs_profile_get",
     "egs_profile_reset", "egs_get_stream", "egs_rounds_stats", "egs_mix64",
 ]
@@ -79,6 +79,7 @@ def load(build: bool = True):
     L.egs_pod_known.argtypes = [vp, u64]
     L.egs_pod_released.argtypes = [vp, u64]
     L.egs_schedule_batch.argtypes = [vp, i32, i32, vp, vp, vp] + [vp] * 6
+    L.egs_schedule_batch_vec.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp] + [vp] * 6
     L.egs_schedule_batch_device.argtypes = [vp, i32, i32, vp, vp] + [vp] * 6
     L.egs_shard_set.argtypes = [vp, i32, i32]
     L.egs_shard_range.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
@@ -242,6 +243,25 @@ class Egs:
         self._ck(self.L.egs_schedule_batch(self.h, mode, P, _p(c_off), _p(units), _p(u), _p(out["node"]),
                                            _p(out["status"]), _p(out["alloc_mask"]), _p(out["fit_count"]),
                                            _p(out["fit_digest"]), _p(out["score_digest"])), "egs_schedule_batch")
+        return out
+
+    def schedule_batch_vec(self, c_off: np.ndarray, units: np.ndarray, vec_pods: int, uids: Optional[np.ndarray] = None):
+        """schedule_batch + the full fit / score vectors of the first `vec_pods` pods ([vec_pods, N] each)."""
+        P = len(c_off) - 1
+        c_off = np.ascontiguousarray(c_off, np.int32)
+        units = np.ascontiguousarray(units, np.int32)
+        vec_pods = min(vec_pods, P)
+        out = dict(node=np.zeros(P, np.int32), status=np.zeros(P, np.int32),
+                   alloc_mask=np.zeros((P, 4), np.uint8), fit_count=np.zeros(P, np.int32),
+                   fit_digest=np.zeros(P, np.uint64), score_digest=np.zeros(P, np.uint64),
+                   vec_fit=np.zeros((max(vec_pods, 1), self.max_nodes), np.uint8),
+                   vec_score=np.zeros((max(vec_pods, 1), self.max_nodes), np.int32))
+        u = None if uids is None else np.ascontiguousarray(uids, np.uint64)
+        self._ck(self.L.egs_schedule_batch_vec(self.h, P, _p(c_off), _p(units), _p(u), vec_pods, _p(out["vec_fit"]),
+                                               _p(out["vec_score"]), _p(out["node"]), _p(out["status"]),
+                                               _p(out["alloc_mask"]), _p(out["fit_count"]), _p(out["fit_digest"]),
+                                               _p(out["score_digest"])), "egs_schedule_batch_vec")
+        out["vec_fit"], out["vec_score"] = out["vec_fit"][:vec_pods], out["vec_score"][:vec_pods]
         return out
 
     def schedule_batch_device(self, c_off: np.ndarray, units: np.ndarray, dptrs: Sequence[int],

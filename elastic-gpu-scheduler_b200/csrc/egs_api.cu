@@ -65,6 +65,7 @@ struct egs_handle {
   // batch outputs
   int32_t *d_o_node = nullptr, *d_o_status = nullptr, *d_o_fit = nullptr; uint8_t *d_o_alloc = nullptr;
   unsigned long long *d_o_fd = nullptr, *d_o_sd = nullptr; int out_cap = 0;
+  uint8_t *d_vec_fit = nullptr; int32_t *d_vec_score = nullptr; size_t vec_cap = 0; int vec_pods = 0;   // egs_schedule_batch_vec
   // profiling
   int64_t k_launches[EGS_K_COUNT] = {0}; double k_ms[EGS_K_COUNT] = {0}; int timing = 0;
   RoundsState rounds;
@@ -286,7 +287,7 @@ extern "C" int egs_destroy(egs_handle *h) {
   rounds_free(&h->rounds);
   void *dev[] = {h->d_core, h->d_mem, h->d_mem_total, h->d_st, h->d_sc, h->d_al, h->d_partials, h->d_ticket, h->d_snap_core, h->d_snap_mem, h->d_snap_total,
                  h->d_result, h->d_ids, h->d_fit, h->d_score, h->d_ev_fit, h->d_ev_score, h->d_ev_gpu, h->d_flush,
-                 h->d_o_node, h->d_o_status, h->d_o_fit, h->d_o_alloc, h->d_o_fd, h->d_o_sd};
+                 h->d_o_node, h->d_o_status, h->d_o_fit, h->d_o_alloc, h->d_o_fd, h->d_o_sd, h->d_vec_fit, h->d_vec_score};
   for (void *p : dev) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -753,7 +754,9 @@ static int batch_rescan(egs_handle *h, int P, const int32_t *c_off, const egs_un
     a.core = h->d_core; a.mem = h->d_mem; a.mem_total = h->d_mem_total; a.core_w = h->d_core; a.mem_w = h->d_mem;
     a.n = h->max_nodes; a.policy = h->policy; a.req = make_req(C, u); a.t = table(h, slots[p]);
     a.all_st = h->d_st; a.slot_stride = (size_t)h->n_pad; a.n_slots = (int)h->shapes.size();
-    a.vec_fit = nullptr; a.vec_score = nullptr; a.partials = h->d_partials; a.ticket = h->d_ticket;
+    a.vec_fit = p < h->vec_pods ? h->d_vec_fit + (size_t)p * h->max_nodes : nullptr;
+    a.vec_score = p < h->vec_pods ? h->d_vec_score + (size_t)p * h->max_nodes : nullptr;
+    a.partials = h->d_partials; a.ticket = h->d_ticket;
     a.pod = p; a.out = out; a.do_bind = 1;
     if (is_single(C, u)) k_pass<true><<<grid, PASS_THREADS, 0, h->stream>>>(a);
     else k_pass<false><<<grid, PASS_THREADS, 0, h->stream>>>(a);
@@ -848,6 +851,34 @@ extern "C" int egs_schedule_batch(egs_handle *h, int mode, int n_pods, const int
   PodOut o; o.node = out_node; o.status = out_status; o.alloc = out_alloc_mask; o.fit_count = out_fit_count;
   o.fit_digest = (unsigned long long *)out_fit_digest; o.score_digest = (unsigned long long *)out_score_digest;
   return batch_common(h, mode, n_pods, c_off, units, uids, o, false);
+}
+
+extern "C" int egs_schedule_batch_vec(egs_handle *h, int n_pods, const int32_t *c_off, const egs_unit *units,
+                                      const uint64_t *uids, int vec_pods, uint8_t *out_vec_fit, int32_t *out_vec_score,
+                                      int32_t *out_node, int32_t *out_status, uint8_t *out_alloc_mask,
+                                      int32_t *out_fit_count, uint64_t *out_fit_digest, uint64_t *out_score_digest) {
+  if (!h || vec_pods < 0 || (vec_pods > 0 && (!out_vec_fit || !out_vec_score))) return EGS_ERR_BAD_ARG;
+  Guard g(h);
+  if (h->world > 1) return fail(h, EGS_ERR_BAD_ARG, "egs_schedule_batch_vec is single-shard");
+  vec_pods = std::min(vec_pods, n_pods);
+  const size_t cells = (size_t)vec_pods * h->max_nodes;
+  if (cells > h->vec_cap) {
+    if (h->d_vec_fit) { cudaFree(h->d_vec_fit); cudaFree(h->d_vec_score); h->d_vec_fit = nullptr; h->d_vec_score = nullptr; h->vec_cap = 0; }
+    CK(h, cudaMalloc(&h->d_vec_fit, cells));
+    CK(h, cudaMalloc(&h->d_vec_score, cells * sizeof(int32_t)));
+    h->vec_cap = cells;
+  }
+  PodOut o; o.node = out_node; o.status = out_status; o.alloc = out_alloc_mask; o.fit_count = out_fit_count;
+  o.fit_digest = (unsigned long long *)out_fit_digest; o.score_digest = (unsigned long long *)out_score_digest;
+  h->vec_pods = vec_pods;
+  const int rc = batch_common(h, EGS_MODE_RESCAN, n_pods, c_off, units, uids, o, false);
+  h->vec_pods = 0;
+  if (rc != EGS_OK) return rc;
+  if (cells) {
+    CK(h, cudaMemcpy(out_vec_fit, h->d_vec_fit, cells, cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(out_vec_score, h->d_vec_score, cells * sizeof(int32_t), cudaMemcpyDeviceToHost));
+  }
+  return EGS_OK;
 }
 
 extern "C" int egs_schedule_batch_device(egs_handle *h, int mode, int n_pods, const int32_t *h_c_off,

@@ -216,6 +216,73 @@ EGS_HD bool trade_general(const int (&c)[EGS_G], const int (&m)[EGS_G], int mem_
   return t.found;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Leaf-parallel form of the general Trade (the resolver evaluates the leaves of one node across the lanes of a
+// warp).  The DFS of gpu.go:72-123 branches only at containers with GPUCount == 0 (one GPU each, tried in index
+// order); whole-GPU containers take the first `cnt` free GPUs of the rows as mutated so far, without branching
+// (gpu.go:95-109).  A leaf is therefore the tuple of GPU digits of the branching containers; DFS order ==
+// lexicographic order with the FIRST branching container most significant, and "the last maximal leaf wins"
+// (gpu.go:85) == the maximal (score, leaf index).  Digits are `bits` wide; a digit that names a GPU the node does
+// not have meets a PAD row and fails CanAllocate like any other infeasible choice.
+// Returns the leaf's score (>= 0) and its Allocated masks, or -1 when the leaf is infeasible.
+// ---------------------------------------------------------------------------------------------
+EGS_HD int trade_leaf_eval(const int (&c0)[EGS_G], const int (&m0)[EGS_G], int mem_total, const Req &r, int policy,
+                           int bits, int nbranch, int leaf, uint32_t &masks_out) {
+  int c[EGS_G], m[EGS_G];
+#pragma unroll
+  for (int g = 0; g < EGS_G; g++) { c[g] = c0[g]; m[g] = m0[g]; }
+  uint32_t masks = 0, used = 0;
+  int j = 0;                                                  // index among the branching containers
+  for (int i = 0; i < r.C; i++) {
+    if (r.cnt[i] > 0) {                                       // gpu.go:95-109 with GetFreeGPUs gpu.go:193-202
+      uint32_t fm = 0; int nf = 0;
+#pragma unroll
+      for (int g = 0; g < EGS_G; g++) {
+        const bool fr = nf < r.cnt[i] && c[g] == EGS_CORE_PER_GPU && m[g] == mem_total;
+        fm |= fr ? (1u << g) : 0u; nf += fr ? 1 : 0;
+      }
+      if (nf < r.cnt[i]) return -1;
+#pragma unroll
+      for (int g = 0; g < EGS_G; g++) { const bool t = (fm >> g) & 1u; c[g] = t ? 0 : c[g]; m[g] = t ? 0 : m[g]; }   // Add gpu.go:32-34
+      masks |= fm << (8 * i);
+      if (EGS_POPC(fm) == 1) used |= fm;
+    } else {                                                  // gpu.go:110-122
+      const int gi = (leaf >> (bits * (nbranch - 1 - j))) & ((1 << bits) - 1);
+      j++;
+      int cg = EGS_PAD, mg = EGS_PAD;
+#pragma unroll
+      for (int g = 0; g < EGS_G; g++) { cg = g == gi ? c[g] : cg; mg = g == gi ? m[g] : mg; }
+      if (!(cg >= r.core[i] && mg >= r.mem[i])) return -1;   // CanAllocate gpu.go:55 (PAD rows fail)
+#pragma unroll
+      for (int g = 0; g < EGS_G; g++) { c[g] -= g == gi ? r.core[i] : 0; m[g] -= g == gi ? r.mem[i] : 0; }
+      masks |= (1u << gi) << (8 * i);
+      used |= 1u << gi;
+    }
+  }
+  masks_out = masks;
+  if (policy != EGS_BINPACK) return 0;                        // Spread.Rate rater.go:56-59
+  const int k = EGS_POPC(used);                               // rater.go:19-30
+  int cmin = INT32_MAX, cmax = INT32_MIN, mmin = INT32_MAX, mmax = INT32_MIN;
+#pragma unroll
+  for (int g = 0; g < EGS_G; g++) {
+    const bool real = c0[g] != EGS_PAD;
+    cmin = real ? EGS_MIN(cmin, c[g]) : cmin; cmax = real ? EGS_MAX(cmax, c[g]) : cmax;
+    mmin = real ? EGS_MIN(mmin, m[g]) : mmin; mmax = real ? EGS_MAX(mmax, m[g]) : mmax;
+  }
+  const int range = (mmax + cmax - mmin - cmin) / 2;
+  return range / (k + 1) * 100;
+}
+// geometry of the leaf space of request r on a node with the given rows
+EGS_HD void trade_leaf_space(const int (&c0)[EGS_G], const Req &r, int &bits, int &nbranch, int &nleaf) {
+  int gcount = 0;
+#pragma unroll
+  for (int g = 0; g < EGS_G; g++) gcount += c0[g] != EGS_PAD ? 1 : 0;
+  bits = gcount <= 1 ? 0 : gcount <= 2 ? 1 : gcount <= 4 ? 2 : 3;
+  nbranch = 0;
+  for (int i = 0; i < r.C; i++) nbranch += r.cnt[i] > 0 ? 0 : 1;
+  nleaf = 1 << (bits * nbranch);
+}
+
 // One container, fractional, non-negative: the shape every BASELINE config except config 3 uses.
 __host__ __device__ __forceinline__ bool req_is_single(const Req &r) {
   return r.C == 1 && r.cnt[0] == 0 && r.core[0] >= 0 && r.mem[0] >= 0;

@@ -406,6 +406,10 @@ struct MwSmem {
   unsigned pmask[NS][NT / 32];       // tracked slots whose option is ABSENT: Trade at the shape's next pod
   int afit[NS], bh_d[NS], dry[NS], observed[NS], xbest_t[NS], hv_nT[NS], hpay_node[NS];
   int lm_seen[NS];                   // lmax[s] covers the slots [0, lm_seen[s]); -1: to be rebuilt
+  // ticket-warp engine: per shape, pods the ticket warp has finished / pods the helper has digested (+ prepared the next)
+  int seq_done[NS], seq_ready[NS];
+  alignas(16) int pkg[NS][16];       // helper -> ticket warp: what the next pod of the shape needs (see PK_*)
+  alignas(16) int evt[NS][8];        // ticket warp -> helper: what the last pod of the shape did (see EV_*)
   int pu[NS];                        // summary of pmask[s]: -1 none, t >= 0 exactly slot t, -2 unknown / several
   int rq_single[NS], rq_core[NS], rq_mem[NS]; uint32_t rq_cmask[NS];
   uint8_t st[NS][NT];                // OPT_*
@@ -448,6 +452,11 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 }
 __device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
+__device__ __forceinline__ int4 ld_vol4(const int *p) {         // 16-byte volatile load from shared memory
+  int4 v;
+  asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
 
 template <class SM>
 __device__ __forceinline__ unsigned hset_slot(uint32_t node) {
@@ -552,6 +561,29 @@ __device__ __forceinline__ const char *head_payload(const SM &S, const MwArgs &a
   return a.bufs + (size_t)d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + S.cur[s][d]) * a.L.cand_bytes;
 }
 
+// General Trade of request r on the tracked slot whose rows are (rc, rm): the DFS leaves spread over the lanes
+// (trade_leaf_eval), the winner = maximal (score, leaf index).  Warp-uniform result.
+__device__ __forceinline__ bool trade_warp(const int *rc, const int *rm, int mem_total, const Req &r, int policy, int lane,
+                                           int &score, uint32_t &masks) {
+  int c[EGS_G], m[EGS_G];
+#pragma unroll
+  for (int g = 0; g < EGS_G; g++) { c[g] = rc[g]; m[g] = rm[g]; }
+  int bits, nbranch, nleaf;
+  trade_leaf_space(c, r, bits, nbranch, nleaf);
+  unsigned long long best = 0;                                   // ((score << 32) | leaf) + 1; 0 = no feasible leaf
+  for (int leaf = lane; leaf < nleaf; leaf += 32) {
+    uint32_t mk;
+    const int sc = trade_leaf_eval(c, m, mem_total, r, policy, bits, nbranch, leaf, mk);
+    if (sc >= 0) { const unsigned long long k = (((unsigned long long)(unsigned)sc << 32) | (unsigned)leaf) + 1ull; best = k > best ? k : best; }
+  }
+  int owner;
+  const unsigned long long win = warp_max_key_fwd(best, owner);
+  if (win == 0) return false;
+  const int leaf = (int)(unsigned)(win - 1ull);
+  score = trade_leaf_eval(c, m, mem_total, r, policy, bits, nbranch, leaf, masks);   // every lane: the winner's masks
+  return true;
+}
+
 // ---- general pod (inside the ticket, whole warp): any shape, any number of pending options, any regime.
 // Returns 0, or the stop reason (nothing was changed for this pod then).
 template <class SM>
@@ -618,16 +650,18 @@ __device__ __noinline__ int general_pod(SM &S, const MwArgs &a, const unsigned l
           }
         }
       } else {
-        const int t = w * 32 + lane;
-        bool ok = false; int sc = 0;
-        if ((word >> lane) & 1u) {
-          uint32_t masks;
-          ok = trade_general(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], a.policy, sc, masks);
-          if (ok) { S.st[s][t] = OPT_CACHED; S.al[s][t] = masks; S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]); }
-          else S.st[s][t] = OPT_UNFIT;
-        }
-        for (unsigned rem = word; rem; rem &= rem - 1) {
-          if (lane == __ffs(rem) - 1 && ok) { S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term_b(S.sbase[t], sc); }
+        for (unsigned rem = word; rem; rem &= rem - 1) {           // one pending node after the other, its DFS leaves over the lanes
+          const int t = w * 32 + __ffs(rem) - 1;
+          int sc = 0; uint32_t masks = 0;
+          const bool ok = trade_warp(S.rc[t], S.rm[t], S.mt[t], S.reqs[s], a.policy, lane, sc, masks);
+          if (lane == 0) {
+            if (ok) {
+              S.st[s][t] = OPT_CACHED; S.al[s][t] = masks; S.tkey[s][t] = cand_key(sc, (uint32_t)S.node[t]);
+              S.afit[s] += 1; S.afd[s] += S.fterm[t]; S.asd[s] += score_term_b(S.sbase[t], sc);
+            } else {
+              S.st[s][t] = OPT_UNFIT;
+            }
+          }
           __syncwarp();
         }
       }
@@ -729,23 +763,17 @@ __device__ __noinline__ int general_pod(SM &S, const MwArgs &a, const unsigned l
   return 0;
 }
 
-template <int NS, int NT>
-__global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  using SM = MwSmem<NS, NT>;
-  SM &S = *reinterpret_cast<SM *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
-  const int D = a.n_shards, rke = a.rke, nw = a.nw;
+// ---- shared by the resolver kernels: round prologue (returns false when the batch is finished) and epilogue
+template <class SM>
+__device__ __noinline__ bool resolve_prologue(SM &S, const MwArgs &a, unsigned long long *lk) {
+  constexpr int NS = (int)(sizeof(S.afit) / sizeof(int)), NT = SM::HS / 2;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  const int D = a.n_shards, rke = a.rke;
   const int ns = a.rd->ns;
-  unsigned long long *lk = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15));   // [ns][D][rke]
-  char *hpay = a.use_hpay ? reinterpret_cast<char *>(lk + (size_t)ns * D * rke) : nullptr;                        // [ns][cand_bytes]
-  // column maxima of tkey: lane L keeps max over the slots t = L (mod 32) of its shapes -> the owner's scan is 1 load
-  unsigned long long *lmax = a.use_lmax ? reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15) + (size_t)ns * D * rke * 8 + (a.use_hpay ? (size_t)ns * a.L.cand_bytes : 0)) : nullptr;   // [ns][32]
-  int *lmax_t = lmax ? reinterpret_cast<int *>(lmax + (size_t)ns * 32) : nullptr;                                 // [ns][32]
   // ---- prologue
   {
     int p0 = a.p0, p_end = a.p_limit;
-    if (a.p0 < 0) { if (ctl_idle(a.ctl)) return; p0 = a.ctl->next_p; p_end = a.ctl->p_end; }
+    if (a.p0 < 0) { if (ctl_idle(a.ctl)) return false; p0 = a.ctl->next_p; p_end = a.ctl->p_end; }
     if (tid == 0) { S.p0 = p0; S.p_end = p_end; S.turn = p0; S.stop = 0; S.stop_reason = 0; S.stop_p = p_end; S.nT = 0; S.n_observed = 0; }
     if (tid < MW_MAX_WARPS) mbar_init(&S.mbar[tid], 1);
   }
@@ -769,6 +797,9 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
     S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd; S.observed[s] = 0; S.pu[s] = -1;
     S.xbest[s] = 0; S.xbest_t[s] = -1; S.hv_nT[s] = -1; S.hpay_node[s] = -1; S.bh[s] = 0; S.bh_d[s] = 0; S.dry[s] = 0;
     S.lm_seen[s] = -1;
+    S.seq_done[s] = 0; S.seq_ready[s] = 0;
+    for (int i = 0; i < 16; i++) S.pkg[s][i] = 0;
+    S.pkg[s][10] = 1;                                             // PK_MODE: the first pod of a shape in a round is a general pod
     if (s < ns) {
       S.reqs[s] = a.rd->reqs[s];
       const Req &r = a.rd->reqs[s];
@@ -788,6 +819,71 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
     S.mono = mono ? 1 : 0;
   }
   __syncthreads();
+  return true;
+}
+
+template <class SM>
+__device__ __noinline__ void resolve_epilogue(SM &S, const MwArgs &a) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const int ns = a.rd->ns;
+  const int p0 = S.p0;
+  // ---- epilogue: write the tracked nodes back (each shard its own nodes)
+  const int nT = S.nT;
+  const int done = S.stop_p - p0;
+  const int nwarps = nthreads >> 5;
+  for (int t = warp; t < nT; t += nwarps) {
+    const int w = S.node[t];
+    if (w < a.lo || w >= a.hi) continue;
+    if (S.dirty[t]) {
+      if (lane < EGS_G) a.core[(size_t)w * EGS_G + lane] = S.rc[t][lane];
+      else if (lane < 2 * EGS_G) a.mem[(size_t)w * EGS_G + lane - EGS_G] = S.rm[t][lane - EGS_G];
+    }
+    for (int s = lane; s < ns; s += 32) {
+      const int slot = a.rd->slot[s];
+      const uint8_t st = S.st[s][t];
+      tb_st(a.tb, slot)[w] = st;
+      if (st == OPT_CACHED || st == OPT_NEW) {
+        tb_sc(a.tb, slot)[w] = key_score(S.tkey[s][t]);
+        uint8_t *alp = tb_al(a.tb, slot);
+        const uint32_t am = S.al[s][t];
+        for (int c = 0; c < S.reqs[s].C; c++) alp[(size_t)c * a.tb.n_pad + w] = (uint8_t)(am >> (8 * c));
+      }
+    }
+    if (S.dirty[t]) {                                            // shapes outside the round set
+      for (int slot = lane; slot < a.tb.n_slots; slot += 32) {
+        bool in_set = false;
+        for (int q = 0; q < ns; q++) in_set |= a.rd->slot[q] == slot;
+        if (in_set) continue;
+        uint8_t *q = tb_st(a.tb, slot) + w;
+        if (*q == OPT_UNFIT) *q = OPT_ABSENT;
+        else if (*q == OPT_NEW) *q = a.obs_pending[slot] ? OPT_CACHED : OPT_ABSENT;
+      }
+    }
+  }
+  for (int s = tid; s < ns; s += nthreads) if (S.observed[s]) a.obs_pending[a.rd->slot[s]] = 1;
+  if (tid == 0) {
+    RoundCtl *c = a.ctl;
+    c->next_p = p0 + done;
+    if (done < 1) c->error = 1;                                  // no progress: the host reports it
+    c->rounds += 1; c->pods += done; c->tracked += nT;
+    c->stops[S.stop ? (S.stop_reason & 3) : 0] += 1;
+  }
+}
+
+template <int NS, int NT>
+__global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using SM = MwSmem<NS, NT>;
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const int D = a.n_shards, rke = a.rke, nw = a.nw;
+  const int ns = a.rd->ns;
+  unsigned long long *lk = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15));   // [ns][D][rke]
+  char *hpay = a.use_hpay ? reinterpret_cast<char *>(lk + (size_t)ns * D * rke) : nullptr;                        // [ns][cand_bytes]
+  // column maxima of tkey: lane L keeps max over the slots t = L (mod 32) of its shapes -> the owner's scan is 1 load
+  unsigned long long *lmax = a.use_lmax ? reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15) + (size_t)ns * D * rke * 8 + (a.use_hpay ? (size_t)ns * a.L.cand_bytes : 0)) : nullptr;   // [ns][32]
+  int *lmax_t = lmax ? reinterpret_cast<int *>(lmax + (size_t)ns * 32) : nullptr;                                 // [ns][32]
+  if (!resolve_prologue(S, a, lk)) return;
   const int p0 = S.p0, p_end = S.p_end;
 #ifdef EGS_RESOLVE_PROF
   long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64();
@@ -1069,49 +1165,269 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
     }
   }
   __syncthreads();
-  // ---- epilogue: write the tracked nodes back (each shard its own nodes)
-  const int nT = S.nT;
-  const int done = S.stop_p - p0;
-  const int nwarps = nthreads >> 5;
-  for (int t = warp; t < nT; t += nwarps) {
-    const int w = S.node[t];
-    if (w < a.lo || w >= a.hi) continue;
-    if (S.dirty[t]) {
-      if (lane < EGS_G) a.core[(size_t)w * EGS_G + lane] = S.rc[t][lane];
-      else if (lane < 2 * EGS_G) a.mem[(size_t)w * EGS_G + lane - EGS_G] = S.rm[t][lane - EGS_G];
-    }
-    for (int s = lane; s < ns; s += 32) {
-      const int slot = a.rd->slot[s];
-      const uint8_t st = S.st[s][t];
-      tb_st(a.tb, slot)[w] = st;
-      if (st == OPT_CACHED || st == OPT_NEW) {
-        tb_sc(a.tb, slot)[w] = key_score(S.tkey[s][t]);
-        uint8_t *alp = tb_al(a.tb, slot);
-        const uint32_t am = S.al[s][t];
-        for (int c = 0; c < S.reqs[s].C; c++) alp[(size_t)c * a.tb.n_pad + w] = (uint8_t)(am >> (8 * c));
-      }
-    }
-    if (S.dirty[t]) {                                            // shapes outside the round set
-      for (int slot = lane; slot < a.tb.n_slots; slot += 32) {
-        bool in_set = false;
-        for (int q = 0; q < ns; q++) in_set |= a.rd->slot[q] == slot;
-        if (in_set) continue;
-        uint8_t *q = tb_st(a.tb, slot) + w;
-        if (*q == OPT_UNFIT) *q = OPT_ABSENT;
-        else if (*q == OPT_NEW) *q = a.obs_pending[slot] ? OPT_CACHED : OPT_ABSENT;
-      }
-    }
-  }
-  for (int s = tid; s < ns; s += nthreads) if (S.observed[s]) a.obs_pending[a.rd->slot[s]] = 1;
-  if (tid == 0) {
-    RoundCtl *c = a.ctl;
-    c->next_p = p0 + done;
-    if (done < 1) c->error = 1;                                  // no progress: the host reports it
-    c->rounds += 1; c->pods += done; c->tracked += nT;
-    c->stops[S.stop ? (S.stop_reason & 3) : 0] += 1;
-  }
+  resolve_epilogue(S, a);
 #ifdef EGS_RESOLVE_PROF
   if (lane == 0 && warp < nw) for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)&a.ctl->prof[i], (unsigned long long)prof[i]);
+#endif
+}
+
+// --------------------------------------------------------------------------------------------
+// k_resolve_tw: ONE ticket warp + one helper warp per shape.
+//
+// Measured on the owner-warp engine above: a warp-to-warp hand-over costs ~300 cycles whatever the mechanism, and
+// the preparation / post-processing of an owner (~4000 cycles) stalls the chain whenever a shape recurs within a
+// few pods.  Here the ordered part of EVERY pod runs on one warp, back to back, with no hand-over; the helper of
+// shape s digests what the ticket warp did to the shape's last pod (option table, aggregates, per-pod outputs) and
+// prepares the next one (best tracked option, list heads, payload prefetch, speculative Trade of the pending
+// option under the rows' seqlock) while the ticket warp works on other shapes.  The ticket warp waits for a helper
+// only when the same shape comes again before its helper is done.
+//   pkg[s] (helper -> ticket warp)   evt[s] (ticket warp -> helper)   seq_ready[s] / seq_done[s] order them.
+// --------------------------------------------------------------------------------------------
+#define PK_BEST 0      // u64
+#define PK_HEAD 2      // u64
+#define PK_TKEY 4      // u64: cand_key of the speculative Trade (0: no fit)
+#define PK_BEST_T 6
+#define PK_U 7
+#define PK_VPRE 8      // seqlock value the speculative Trade saw (-1: none)
+#define PK_AL 9        // Allocated mask of the best tracked option
+#define PK_MODE 10     // 0 fast, 1 general
+#define PK_DRY 11
+#define PK_UND 12      // node id of slot u
+#define PK_BK 13       // folded key of the speculative Trade (-1: no fit)
+#define EV_WIN 0       // u64
+#define EV_P 2
+#define EV_U 3
+#define EV_BK 4
+#define EV_TW 5
+#define EV_FLAGS 6     // 1 from_head, 2 transact ok, 4 general pod (nothing to digest)
+#define EV_MASKS 7
+
+template <int NS, int NT>
+__global__ void __launch_bounds__(32 * (MW_MAX_WARPS + 1), 1) k_resolve_tw(MwArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using SM = MwSmem<NS, NT>;
+  SM &S = *reinterpret_cast<SM *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int D = a.n_shards, rke = a.rke, nh = a.nw;              // helpers: warps 0..nh-1; ticket warp: warp nh (highest id)
+  const int ns = a.rd->ns;
+  unsigned long long *lk = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15));   // [ns][D][rke]
+  char *hpay = a.use_hpay ? reinterpret_cast<char *>(lk + (size_t)ns * D * rke) : nullptr;                        // [ns][cand_bytes]
+  if (!resolve_prologue(S, a, lk)) return;
+  const int p0 = S.p0, p_end = S.p_end;
+  const bool mono = S.mono != 0;
+  const int gl = lane & 7;
+#ifdef EGS_RESOLVE_PROF
+  long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64();
+#endif
+  if (warp == nh) {
+    // =========================================================== the ticket warp
+    int cb = p0 & ~3;
+    uint32_t myword = 0xFFFFFFFFu;
+    auto load_chunk = [&](int base) {
+      const int q = base + 4 * lane;
+      myword = q < p_end ? *reinterpret_cast<const uint32_t *>(a.pod_sidx + q) : 0xFFFFFFFFu;
+    };
+    load_chunk(cb);
+    int reason = 0, p = p0;
+    for (; p < p_end; p++) {
+      if (p - cb >= 128) { cb += 128; load_chunk(cb); }
+      const int i = p - cb;
+      const int s = (int)((__shfl_sync(0xffffffffu, myword, i >> 2) >> (8 * (i & 3))) & 0xFFu);
+      const int k = S.seq_done[s];
+      while (ld_vol(&S.seq_ready[s]) != k) { }                   // the helper has digested this shape's previous pod
+      PROF_T(1)
+      const int4 q0 = ld_vol4(&S.pkg[s][0]), q1 = ld_vol4(&S.pkg[s][4]), q2 = ld_vol4(&S.pkg[s][8]), q3 = ld_vol4(&S.pkg[s][12]);
+      int flags = 0, bk = q3.y, tw = -1; uint32_t masks = 0; unsigned long long win = 0;
+      const int u = q1.w;
+      if (q2.z) {                                                 // general pod: the whole warp, any shape / state
+        reason = general_pod(S, a, lk, hpay, lane, p, s, ns);
+        if (reason) break;
+        flags = 4;
+        PROF_C(9, 1)
+      } else {
+        const int uu = max(u, 0);
+        const int vnow = S.ver[uu];
+        const unsigned long long xb = S.xbest[s];
+        const int xt = S.xbest_t[s];
+        const int rq_c = S.rq_core[s], rq_m = S.rq_mem[s];
+        unsigned long long tradekey = ((unsigned long long)(unsigned)q1.y << 32) | (unsigned)q1.x;
+        if (u >= 0 && vnow != q2.x) {                             // the node's rows changed since the helper's Trade
+          const int4 c0 = *reinterpret_cast<const int4 *>(&S.rc[uu][0]), c1 = *reinterpret_cast<const int4 *>(&S.rc[uu][4]);
+          const int4 m0 = *reinterpret_cast<const int4 *>(&S.rm[uu][0]), m1 = *reinterpret_cast<const int4 *>(&S.rm[uu][4]);
+          const int c[EGS_G] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+          const int m[EGS_G] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+          bk = trade_lanes(c, m, gl, rq_c, rq_m, a.policy);
+          const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
+          tradekey = bk >= 0 ? cand_key(sc, (uint32_t)q3.x) : 0ull;
+          PROF_C(14, 1)
+        }
+        unsigned long long best = ((unsigned long long)(unsigned)q0.y << 32) | (unsigned)q0.x;
+        const unsigned long long head = ((unsigned long long)(unsigned)q0.w << 32) | (unsigned)q0.z;
+        tw = q1.z; masks = (uint32_t)q2.y;
+        if (xb > best) { best = xb; tw = xt; masks = 0; }
+        if (tradekey > best) { best = tradekey; tw = u; masks = 1u << (bk & 7); }
+        const bool from_head = head > best;
+        win = from_head ? head : best;
+        int nT = 0;
+        if (q2.w) reason = 3;                                     // a truncated list ran dry
+        else if (from_head) { nT = S.nT; if (nT >= NT) reason = 2; }
+        if (reason) break;
+        if (win != 0) {
+          if (from_head) {
+            tw = nT;
+            const uint32_t w = key_node(win);
+            install_slot(S, a, head_payload(S, a, hpay, s, w), tw, w, ns, s, lane);
+            __syncwarp();
+            masks = S.al[s][tw] & 0xFFu;
+            flags |= 1;
+            PROF_C(11, 1)
+          } else if (masks == 0) {
+            masks = S.al[s][tw] & 0xFFu;                          // a slot another shape installed
+          }
+          const int g = __ffs(masks) - 1;
+          const int cc = S.rc[tw][g], mm = S.rm[tw][g];
+          const int ok = (cc >= rq_c && mm >= rq_m) ? 1 : 0;      // GPUs.Transact gpu.go:164-171
+          __syncwarp();
+          if (lane == 0) {
+            if (ok) { const int v = S.ver[tw]; st_vol(&S.ver[tw], v + 1); S.rc[tw][g] = cc - rq_c; S.rm[tw][g] = mm - rq_m; st_vol(&S.ver[tw], v + 2); }
+            S.dirty[tw] = 1;
+            if (from_head) { __threadfence_block(); st_vol(&S.nT, nT + 1); }
+          }
+          flags |= ok ? 2 : 0;
+          if (!ok) masks = 0;
+        }
+        if (lane == 0 && xb != 0) { S.xbest[s] = 0; S.xbest_t[s] = -1; }
+        PROF_C(6, 1)
+      }
+      // ---- tell the helper (mailbox, then the sequence number, then wake it)
+      if (lane == 0) {
+        *reinterpret_cast<int4 *>(&S.evt[s][0]) = make_int4((int)(unsigned)win, (int)(unsigned)(win >> 32), p, u);
+        *reinterpret_cast<int4 *>(&S.evt[s][4]) = make_int4(bk, tw, flags, (int)masks);
+        __threadfence_block();
+        st_vol(&S.seq_done[s], k + 1);
+        mbar_arrive(&S.mbar[s % nh]);
+      }
+      __syncwarp();
+#ifdef EGS_RESOLVE_PROF
+      { const long long n_ = clock64(); prof[(flags & 4) ? 4 : (flags & 1) ? 5 : 2] += n_ - tprev; tprev = n_; }
+#endif
+    }
+    // ---- the round ends before pod p (reason != 0) or all pods are done: wake every helper
+    if (lane == 0) { S.stop_reason = reason; S.stop_p = p; __threadfence_block(); st_vol(&S.stop, reason ? 1 : 2); }
+    __syncwarp();
+    if (lane < nh) mbar_arrive(&S.mbar[lane]);
+  } else if (warp < nh) {
+    // =========================================================== a helper: shapes s with s % nh == warp
+    unsigned ph = 0;
+    while (true) {
+      bool progressed = false;
+      const int stopping = ld_vol(&S.stop);
+      for (int s = warp; s < ns; s += nh) {
+        const int k = S.seq_ready[s];
+        if (ld_vol(&S.seq_done[s]) == k) continue;
+        __threadfence_block();
+        progressed = true;
+        // ---- digest pod k of shape s
+        const int4 e0 = ld_vol4(&S.evt[s][0]), e1 = ld_vol4(&S.evt[s][4]);
+        const int flags = e1.z;
+        if (!(flags & 4)) {
+          const unsigned long long win = ((unsigned long long)(unsigned)e0.y << 32) | (unsigned)e0.x;
+          const int p = e0.z, u = e0.w, bk = e1.x, tw = e1.y;
+          const int uu = max(u, 0);
+          const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
+          const int fit = S.afit[s] + (bk >= 0);
+          const unsigned long long fd = S.afd[s] + (bk >= 0 ? S.fterm[uu] : 0ull);
+          const unsigned long long sd = S.asd[s] + (bk >= 0 ? score_term_b(S.sbase[uu], sc) : 0ull);
+          if (lane == 0) {
+            if (u >= 0 && u != tw) {                              // the pod's filter Traded slot u
+              if (bk >= 0) { S.st[s][u] = OPT_CACHED; S.al[s][u] = 1u << (bk & 7); S.tkey[s][u] = cand_key(sc, (uint32_t)S.node[u]); }
+              else S.st[s][u] = OPT_UNFIT;
+              S.pmask[s][u >> 5] &= ~(1u << (u & 31));
+            }
+            int o_node = -1, o_status = EGS_ERR_NOFIT;
+            if (win != 0) {                                       // node.go:90-92: the entry is consumed
+              S.st[s][tw] = OPT_ABSENT; S.tkey[s][tw] = 0; S.pmask[s][tw >> 5] |= 1u << (tw & 31);
+              S.afit[s] = fit - 1; S.afd[s] = fd - S.fterm[tw]; S.asd[s] = sd - score_term_b(S.sbase[tw], key_score(win));
+              S.pu[s] = tw;
+              o_node = S.node[tw]; o_status = (flags & 2) ? EGS_OK : EGS_ERR_TRANSACT;
+            } else {
+              S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd;
+              S.pu[s] = -1;
+            }
+            if (a.out.node) a.out.node[p] = o_node;
+            if (a.out.status) a.out.status[p] = o_status;
+            if (a.out.fit_count) a.out.fit_count[p] = fit;
+            if (a.out.fit_digest) a.out.fit_digest[p] = fd;
+            if (a.out.score_digest) a.out.score_digest[p] = sd;
+            if (a.out.alloc) reinterpret_cast<uint32_t *>(a.out.alloc)[p] = (uint32_t)e1.w;
+          }
+          __syncwarp();
+        }
+        // ---- prepare pod k+1 of shape s
+        int payload_d = -1, payload_c = 0; unsigned long long head = 0;
+        if (!stopping) {
+          maintain_heads(S, lk, D, rke, s, lane, false);
+          head = S.bh[s];
+          const int pu = S.pu[s];
+          const bool fast = mono && S.rq_single[s] && pu != -2 && ld_vol(&S.n_observed) == ns;
+          unsigned long long pre_best = 0, tradekey = 0; int pre_t = -1, v_pre = -1, bk_pre = -1; uint32_t pre_al = 0, und = 0;
+          if (fast) {
+            const int pre_nT = ld_vol(&S.nT);
+            __threadfence_block();
+            unsigned long long b = 0; int bt = -1;
+#pragma unroll 4
+            for (int t = lane; t < pre_nT; t += 32) { const unsigned long long kk = S.tkey[s][t]; if (kk > b) { b = kk; bt = t; } }
+            int owner;
+            pre_best = warp_max_key_fwd(b, owner);
+            pre_t = __shfl_sync(0xffffffffu, bt, owner);
+            pre_al = pre_t >= 0 ? (S.al[s][pre_t] & 0xFFu) : 0u;
+            if (pu >= 0) {                                        // Trade of the pending option on the rows as they are NOW
+              und = (uint32_t)S.node[pu];
+              v_pre = ld_vol(&S.ver[pu]);
+              int c[EGS_G], m[EGS_G];
+#pragma unroll
+              for (int g = 0; g < EGS_G; g++) { c[g] = ld_vol(&S.rc[pu][g]); m[g] = ld_vol(&S.rm[pu][g]); }
+              bk_pre = trade_lanes(c, m, gl, S.rq_core[s], S.rq_mem[s], a.policy);
+              if ((v_pre & 1) || ld_vol(&S.ver[pu]) != v_pre) v_pre = -1;   // a bind was writing the rows meanwhile
+              const int sc = (bk_pre >= 0 && a.policy == EGS_BINPACK) ? (bk_pre >> 3) * 100 : 0;
+              tradekey = bk_pre >= 0 ? cand_key(sc, und) : 0ull;
+            }
+          }
+          if (lane == 0) {
+            *reinterpret_cast<int4 *>(&S.pkg[s][0]) = make_int4((int)(unsigned)pre_best, (int)(unsigned)(pre_best >> 32), (int)(unsigned)head, (int)(unsigned)(head >> 32));
+            *reinterpret_cast<int4 *>(&S.pkg[s][4]) = make_int4((int)(unsigned)tradekey, (int)(unsigned)(tradekey >> 32), pre_t, pu);
+            *reinterpret_cast<int4 *>(&S.pkg[s][8]) = make_int4(v_pre, (int)pre_al, fast ? 0 : 1, S.dry[s]);
+            *reinterpret_cast<int4 *>(&S.pkg[s][12]) = make_int4((int)und, bk_pre, 0, 0);
+          }
+          if (hpay && head != 0 && S.hpay_node[s] != (int)key_node(head)) { payload_d = S.bh_d[s]; payload_c = S.cur[s][payload_d]; }
+        }
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); st_vol(&S.seq_ready[s], k + 1); }
+        __syncwarp();
+        // ---- after the hand-back: payload of the best head -> shared memory (a head-win finds it there)
+        if (payload_d >= 0) {
+          if (lane == 0) st_vol(&S.hpay_node[s], -1);
+          __syncwarp();
+          const int4 *src = reinterpret_cast<const int4 *>(a.bufs + (size_t)payload_d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + payload_c) * a.L.cand_bytes);
+          int4 *dst = reinterpret_cast<int4 *>(hpay + (size_t)s * a.L.cand_bytes);
+          for (int i = lane; i < a.L.cand_bytes / 16; i += 32) dst[i] = src[i];
+          __syncwarp();
+          if (lane == 0) { __threadfence_block(); st_vol(&S.hpay_node[s], (int)key_node(head)); }
+          __syncwarp();
+        }
+        PROF_T(0)
+      }
+      if (!progressed) {
+        if (stopping) break;
+        while (!mbar_try_wait(&S.mbar[warp], ph)) { if (ld_vol(&S.stop)) break; }
+        ph ^= 1u;
+      }
+    }
+  }
+  __syncthreads();
+  resolve_epilogue(S, a);
+#ifdef EGS_RESOLVE_PROF
+  if (lane == 0 && warp <= nh) for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)&a.ctl->prof[i], (unsigned long long)prof[i]);
 #endif
 }
 

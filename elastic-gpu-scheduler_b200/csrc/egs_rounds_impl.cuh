@@ -91,6 +91,9 @@ static int rounds_ensure(egs_handle *h, int P, const BufLayout &L) {
     CK(h, cudaFuncSetAttribute(k_resolve_mw<16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
     CK(h, cudaFuncSetAttribute(k_resolve_mw<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
     CK(h, cudaFuncSetAttribute(k_resolve_mw<RSMAX, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
+    CK(h, cudaFuncSetAttribute(k_resolve_tw<16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
+    CK(h, cudaFuncSetAttribute(k_resolve_tw<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
+    CK(h, cudaFuncSetAttribute(k_resolve_tw<RSMAX, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
   }
   const size_t need = (size_t)L.bytes * RD;
   if (need > R.bufs_cap) {
@@ -149,7 +152,11 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   }
   const bool one_set = (int)batch_shapes.size() <= RSMAX;
   const int ns_cfg = one_set ? (int)batch_shapes.size() : RSMAX;
-  const MwConfig cfg = mw_config(ns_cfg);
+  MwConfig cfg = mw_config(ns_cfg);
+  // sharded: every shard contributes its own list; the resolver holds about the same number of candidates per
+  // shape in total, so each shard gathers (and ships) fewer
+  if (h->world >= 4) cfg.rkm = std::min(cfg.rkm, 32);
+  else if (h->world >= 2) cfg.rkm = std::min(cfg.rkm, 64);
   const BufLayout L = make_layout(ns_cfg, cfg.rkm);
   TRY(rounds_ensure(h, P, L));
 
@@ -196,7 +203,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   int rke = cfg.rkm;
   auto env_int = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
   const int use_hpay = cfg.inst != 2 ? env_int("EGS_MW_HPAY", 2) : 0;   // prefetched candidate payload per shape (2: cp.async)
-  const int use_lmax = cfg.inst != 2 ? env_int("EGS_MW_LMAX", 1) : 0;   // cached column maxima of the tracked keys
+  const int use_lmax = cfg.inst != 2 ? env_int("EGS_MW_LMAX", 0) : 0;   // cached column maxima of the tracked keys
   const size_t hp_bytes = (use_hpay ? (size_t)ns_cfg * L.cand_bytes : 0) + (use_lmax ? (size_t)ns_cfg * 32 * 12 : 0);
   {
     const size_t avail = MW_SMEM_MAX - cfg.smem_struct - hp_bytes;
@@ -205,6 +212,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
     if (rke < 4) return fail(h, EGS_ERR_BAD_ARG, "rounds: shape set too large for the resolver's shared memory");
   }
   const int nw = std::max(1, std::min(ns_cfg, env_int("EGS_MW_WARPS", MW_MAX_WARPS)));
+  const int engine_tw = env_int("EGS_RESOLVER_TW", 0);
   const size_t smem = cfg.smem_struct + (size_t)ns_cfg * D * rke * 8 + hp_bytes;
 
   SelectArgs sa; MergeArgs ma; MwArgs ra;
@@ -227,9 +235,15 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
     if (h->world > 1)
       NCK(h, nccl_api()->AllGather(R.d_bufs + (size_t)h->rank * L.bytes, R.d_bufs, (size_t)L.bytes, ncclChar, (ncclComm_t)R.comm, h->stream));
     if (h->timing) CK(h, cudaEventRecord(ev[2], h->stream));
-    if (cfg.inst == 0) k_resolve_mw<16, 512><<<1, 32 * nw, smem, h->stream>>>(ra);
-    else if (cfg.inst == 1) k_resolve_mw<32, 256><<<1, 32 * nw, smem, h->stream>>>(ra);
-    else k_resolve_mw<RSMAX, 128><<<1, 32 * nw, smem, h->stream>>>(ra);
+    if (engine_tw) {                                            // one ticket warp + nw helper warps
+      if (cfg.inst == 0) k_resolve_tw<16, 512><<<1, 32 * (nw + 1), smem, h->stream>>>(ra);
+      else if (cfg.inst == 1) k_resolve_tw<32, 256><<<1, 32 * (nw + 1), smem, h->stream>>>(ra);
+      else k_resolve_tw<RSMAX, 128><<<1, 32 * (nw + 1), smem, h->stream>>>(ra);
+    } else {                                                    // one owner warp per shape, ticket passed between them
+      if (cfg.inst == 0) k_resolve_mw<16, 512><<<1, 32 * nw, smem, h->stream>>>(ra);
+      else if (cfg.inst == 1) k_resolve_mw<32, 256><<<1, 32 * nw, smem, h->stream>>>(ra);
+      else k_resolve_mw<RSMAX, 128><<<1, 32 * nw, smem, h->stream>>>(ra);
+    }
     if (h->timing) CK(h, cudaEventRecord(ev[3], h->stream));
     h->k_launches[EGS_K_SELECT] += 1; h->k_launches[EGS_K_MERGE] += 1; h->k_launches[EGS_K_RESOLVE] += 1;
     return EGS_OK;

@@ -28,6 +28,26 @@ int egsdh_trade(const int32_t *core, const int32_t *mem, int mem_total, int C, c
   *score = sc; *masks = mk;
   return ok ? 1 : 0;
 }
+// the leaf-parallel Trade the resolver runs across a warp, serially: max over (score, leaf index)
+int egsdh_trade_leaves(const int32_t *core, const int32_t *mem, int mem_total, int C, const egs_unit *units, int policy,
+                       int32_t *score, uint32_t *masks) {
+  int c[EGS_G], m[EGS_G];
+  rows(core, mem, c, m);
+  const Req r = make_req(C, units);
+  int bits, nbranch, nleaf;
+  trade_leaf_space(c, r, bits, nbranch, nleaf);
+  long long best = -1; uint32_t bm = 0;
+  for (int leaf = 0; leaf < nleaf; leaf++) {
+    uint32_t mk = 0;
+    const int sc = trade_leaf_eval(c, m, mem_total, r, policy, bits, nbranch, leaf, mk);
+    if (sc < 0) continue;
+    const long long key = ((long long)sc << 20) | leaf;
+    if (key > best) { best = key; bm = mk; }
+  }
+  if (best < 0) return 0;
+  *score = (int32_t)(best >> 20); *masks = bm;
+  return 1;
+}
 int egsdh_transact(int32_t *core, int32_t *mem, int mem_total, int C, const egs_unit *units, uint32_t masks) {
   const Req r = make_req(C, units);
   return transact_row(core, mem, mem_total, r, masks) ? 1 : 0;

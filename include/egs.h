@@ -176,6 +176,15 @@ int egs_schedule_batch(egs_handle *h, int mode, int n_pods, const int32_t *c_off
                        int32_t *out_node, int32_t *out_status, uint8_t *out_alloc_mask,
                        int32_t *out_fit_count, uint64_t *out_fit_digest, uint64_t *out_score_digest);
 
+/* The same driver rule with the FULL per-pod vectors materialised for pods [0, vec_pods): out_vec_fit[p*N + n] in {0,1}
+ * and out_vec_score[p*N + n] (0 for unfit nodes) over all N = max_nodes nodes in index order -- what Assume returns
+ * as filteredNodes and priority.go:26-39 as the HostPriorityList.  Runs the one-pass-per-pod engine (EGS_MODE_RESCAN,
+ * single shard); the six per-pod outputs are as in egs_schedule_batch. */
+int egs_schedule_batch_vec(egs_handle *h, int n_pods, const int32_t *c_off, const egs_unit *units, const uint64_t *uids,
+                           int vec_pods, uint8_t *out_vec_fit, int32_t *out_vec_score,
+                           int32_t *out_node, int32_t *out_status, uint8_t *out_alloc_mask,
+                           int32_t *out_fit_count, uint64_t *out_fit_digest, uint64_t *out_score_digest);
+
 /* Same loop with every buffer already in device memory (bench `value` leg):
  * d_* are device pointers on the handle's device, laid out as above. */
 int egs_schedule_batch_device(egs_handle *h, int mode, int n_pods, const int32_t *h_c_off,

@@ -18,6 +18,7 @@ def DH():
     import egs_b200
     L = C.CDLL(egs_b200._build.build_devhost())
     L.egsdh_trade.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.egsdh_trade_leaves.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     L.egsdh_transact.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
     L.egsdh_is_single.argtypes = [C.c_int, C.c_void_p]
     for f in ("egsdh_cand_key", "egsdh_fit_term", "egsdh_score_term"):
@@ -69,6 +70,23 @@ def test_kernel_trade_equals_oracle(DH, rows, req, policy, mt):
     want = None if opt is None else (opt.allocated, opt.score)
     assert _trade(DH, rows, mt, req, policy, 0) == want          # the dispatch the kernels use
     assert _trade(DH, rows, mt, req, policy, 1) == want          # general DFS on every request
+
+
+@settings(max_examples=800, deadline=None)
+@given(rows=rows_s, req=st.lists(unit, min_size=1, max_size=4), policy=st.integers(0, 1), mt=st.integers(1, 40))
+def test_leaf_parallel_trade_equals_oracle(DH, rows, req, policy, mt):
+    """trade_leaf_eval / trade_leaf_space (the Trade the resolver spreads over the lanes of a warp, one DFS leaf per
+    lane): the maximal (score, leaf index) over all leaves is the option gpu.go:65-129 returns -- same Allocated,
+    same Score, same 'last maximal leaf wins', including whole-GPU and sentinel containers and 3/5/6/7-GPU nodes."""
+    g = [po.GPU(c, m, 100, mt) for c, m in rows]
+    opt = po.trade(g, po.RATERS[policy], list(req))
+    want = None if opt is None else (opt.allocated, opt.score)
+    core, mem = _pad(rows)
+    u = _units(req)
+    sc, mk = C.c_int32(0), C.c_uint32(0)
+    ok = DH.egsdh_trade_leaves(core.ctypes.data, mem.ctypes.data, mt, len(req), u.ctypes.data, policy, C.byref(sc), C.byref(mk))
+    got = None if not ok else ([[gg for gg in range(8) if (mk.value >> (8 * c + gg)) & 1] for c in range(len(req))], sc.value)
+    assert got == want
 
 
 @settings(max_examples=600, deadline=None)

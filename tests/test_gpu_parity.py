@@ -167,6 +167,30 @@ def test_cfg2_late_windows(K):
     _late_window(2, None, K, 5000)
 
 
+@pytest.mark.parametrize("cfg,n_pods,vec_pods", [(0, None, 8), (1, 10000, 1500), (2, 3000, 600)])
+def test_full_fit_and_score_vectors(cfg, n_pods, vec_pods):
+    """on configs 0-2 the FULL per-pod fit mask and score vector (what /scheduler/filter and
+    /scheduler/priorities return for every candidate node) are compared element-wise with the oracle."""
+    eg = _egs()
+    w = eg.workloads.config(cfg, n_pods=n_pods)
+    if cfg == 0:
+        e = eg.Egs(0, 4)
+        o = oc.OracleC(0)
+        for n in range(4):
+            assert e.node_set_allocatable(n, 200, 32) == 0
+            o.add_node(200, 32)
+    else:
+        e = _gpu_for(w)
+        o = _oracle_for(w)
+    ref = o.schedule_batch(w.c_off, w.units64(), vec_pods=vec_pods)
+    got = e.schedule_batch_vec(w.c_off, w.units, vec_pods)
+    for f in FIELDS:
+        assert np.array_equal(ref[f], got[f]), f
+    assert np.array_equal(ref["vec_fit"], got["vec_fit"])
+    assert np.array_equal(ref["vec_score"], got["vec_score"])
+    assert got["vec_fit"].sum() > 0
+
+
 def test_pressure_small_cluster():
     """Few nodes, many pods: nodes fill up, unfit nodes and stale-option bind failures appear."""
     eg = _egs()
