@@ -25,7 +25,7 @@ SYMBOLS = [
     "egs_node_set_allocatable", "egs_node_set", "egs_state_load", "egs_state_load_bulk", "egs_state_dump",
     "egs_state_snapshot", "egs_state_restore",
     "egs_filter", "egs_score", "egs_bind", "egs_option_peek", "egs_option_dump", "egs_pod_apply", "egs_node_replay_pod", "egs_pod_cancel",
-    "egs_pod_known", "egs_pod_released", "egs_schedule_batch", "egs_schedule_batch_vec", "egs_schedule_batch_device",
+    "egs_mutations_apply", "egs_schedule_batch_mut", "egs_pod_known", "egs_pod_released", "egs_schedule_batch", "egs_schedule_batch_vec", "egs_schedule_batch_device",
     "egs_shard_set", "egs_shard_range", "egs_comm_unique_id", "egs_comm_init", "egs_profile_evaluate", "egs_profile_get",
     "egs_profile_reset", "egs_get_stream", "egs_rounds_stats", "egs_mix64",
 ]
@@ -76,6 +76,8 @@ def load(build: bool = True):
     L.egs_pod_apply.argtypes = [vp, i32, i32, vp, vp, vp, u64]
     L.egs_node_replay_pod.argtypes = [vp, i32, i32, vp, vp, vp, u64]
     L.egs_pod_cancel.argtypes = [vp, i32, i32, vp, vp, vp, u64]
+    L.egs_mutations_apply.argtypes = [vp, i32, vp]
+    L.egs_schedule_batch_mut.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp, vp] + [vp] * 6
     L.egs_pod_known.argtypes = [vp, u64]
     L.egs_pod_released.argtypes = [vp, u64]
     L.egs_schedule_batch.argtypes = [vp, i32, i32, vp, vp, vp] + [vp] * 6
@@ -93,6 +95,25 @@ def load(build: bool = True):
     L.egs_mix64.argtypes = [u64]; L.egs_mix64.restype = u64
     _lib = L
     return L
+
+
+MUTATION_DTYPE = np.dtype([("kind", "<i4"), ("node_id", "<i4"), ("n_containers", "<i4"), ("pad", "<i4"),
+                           ("units", "<i4", (4, 3)), ("n_idx", "i1", (4,)), ("idx", "i1", (4, 8)), ("uid", "<u8")], align=True)
+EGS_MUT_ADD, EGS_MUT_FORGET, EGS_MUT_REPLAY = 0, 1, 2
+
+
+def mutations_array(records) -> np.ndarray:
+    """records: [(kind, node_id, req [(core, mem, count)], alloc [[gpu idx]], uid)] -> egs_mutation[]"""
+    a = np.zeros(max(1, len(records)), MUTATION_DTYPE)
+    for i, (kind, node, req, alloc, uid) in enumerate(records):
+        a[i]["kind"], a[i]["node_id"], a[i]["n_containers"], a[i]["uid"] = kind, node, len(req), uid
+        for c, u in enumerate(req):
+            a[i]["units"][c] = u
+            ids = (alloc[c] if alloc and c < len(alloc) and alloc[c] else [])
+            a[i]["n_idx"][c] = len(ids)
+            for j, g in enumerate(ids):
+                a[i]["idx"][c][j] = g
+    return a
 
 
 def _p(a: Optional[np.ndarray]):
@@ -223,6 +244,23 @@ class Egs:
     def pod_cancel(self, node: int, req, alloc, uid: int) -> int:
         off, idx = _alloc_arrays(alloc)
         return self.L.egs_pod_cancel(self.h, node, len(req), _p(units_array(req)), _p(off), _p(idx), uid)
+
+    def mutations_apply(self, records) -> int:
+        a = mutations_array(records)
+        return self.L.egs_mutations_apply(self.h, len(records), _p(a))
+
+    def schedule_batch_mut(self, c_off, units, mut_at, records, uids=None, mode: int = EGS_MODE_AUTO):
+        P = len(c_off) - 1
+        c_off = np.ascontiguousarray(c_off, np.int32); units = np.ascontiguousarray(units, np.int32)
+        at = np.ascontiguousarray(mut_at, np.int32); a = mutations_array(records)
+        out = dict(node=np.zeros(P, np.int32), status=np.zeros(P, np.int32),
+                   alloc_mask=np.zeros((P, 4), np.uint8), fit_count=np.zeros(P, np.int32),
+                   fit_digest=np.zeros(P, np.uint64), score_digest=np.zeros(P, np.uint64))
+        u = None if uids is None else np.ascontiguousarray(uids, np.uint64)
+        self._ck(self.L.egs_schedule_batch_mut(self.h, mode, P, _p(c_off), _p(units), _p(u), len(records), _p(at), _p(a),
+                                               _p(out["node"]), _p(out["status"]), _p(out["alloc_mask"]), _p(out["fit_count"]),
+                                               _p(out["fit_digest"]), _p(out["score_digest"])), "egs_schedule_batch_mut")
+        return out
 
     def pod_known(self, uid: int) -> bool:
         return bool(self.L.egs_pod_known(self.h, uid))

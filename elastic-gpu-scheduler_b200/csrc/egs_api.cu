@@ -65,6 +65,7 @@ struct egs_handle {
   // batch outputs
   int32_t *d_o_node = nullptr, *d_o_status = nullptr, *d_o_fit = nullptr; uint8_t *d_o_alloc = nullptr;
   unsigned long long *d_o_fd = nullptr, *d_o_sd = nullptr; int out_cap = 0;
+  ApplyOp *d_ops = nullptr; int32_t *d_group_off = nullptr; size_t ops_cap = 0;   // egs_mutations_apply
   uint8_t *d_vec_fit = nullptr; int32_t *d_vec_score = nullptr; size_t vec_cap = 0; int vec_pods = 0;   // egs_schedule_batch_vec
   // profiling
   int64_t k_launches[EGS_K_COUNT] = {0}; double k_ms[EGS_K_COUNT] = {0}; int timing = 0;
@@ -287,7 +288,7 @@ extern "C" int egs_destroy(egs_handle *h) {
   rounds_free(&h->rounds);
   void *dev[] = {h->d_core, h->d_mem, h->d_mem_total, h->d_st, h->d_sc, h->d_al, h->d_partials, h->d_ticket, h->d_snap_core, h->d_snap_mem, h->d_snap_total,
                  h->d_result, h->d_ids, h->d_fit, h->d_score, h->d_ev_fit, h->d_ev_score, h->d_ev_gpu, h->d_flush,
-                 h->d_o_node, h->d_o_status, h->d_o_fit, h->d_o_alloc, h->d_o_fd, h->d_o_sd, h->d_vec_fit, h->d_vec_score};
+                 h->d_o_node, h->d_o_status, h->d_o_fit, h->d_o_alloc, h->d_o_fd, h->d_o_sd, h->d_vec_fit, h->d_vec_score, h->d_ops, h->d_group_off};
   for (void *p : dev) if (p) cudaFree(p);
   if (h->h_result) cudaFreeHost(h->h_result);
   if (h->h_stage) cudaFreeHost(h->h_stage);
@@ -713,6 +714,90 @@ extern "C" int egs_pod_cancel(egs_handle *h, int node_id, int n_containers, cons
   return EGS_OK;
 }
 
+// ------------------------------------------------------------------------------- mutation stream
+// caller holds the lock; pending batch bookkeeping already flushed
+static int mutations_apply_locked(egs_handle *h, int n, const egs_mutation *ops) {
+  if (n < 0 || (n > 0 && !ops)) return EGS_ERR_BAD_ARG;
+  if (n == 0) return EGS_OK;
+  // pass 1: validate everything first (a malformed record applies nothing)
+  for (int i = 0; i < n; i++) {
+    const egs_mutation &m = ops[i];
+    if (m.kind < EGS_MUT_ADD || m.kind > EGS_MUT_REPLAY) return EGS_ERR_BAD_ARG;
+    if (m.node_id < 0) { if (m.kind != EGS_MUT_FORGET) return EGS_ERR_BAD_ARG; continue; }
+    if (m.node_id >= h->max_nodes) return EGS_ERR_BAD_ARG;
+    if (h->h_gpu_count[m.node_id] == 0) return EGS_ERR_NO_NODE;
+    TRY(check_units(m.n_containers, m.units));
+    for (int c = 0; c < m.n_containers; c++) {
+      if (m.n_idx[c] < 0 || m.n_idx[c] > EGS_G) return EGS_ERR_BAD_ARG;
+      for (int j = 0; j < m.n_idx[c]; j++) if (m.idx[c][j] < 0 || m.idx[c][j] >= h->h_gpu_count[m.node_id]) return EGS_ERR_BAD_ARG;
+    }
+  }
+  // pass 2: the podsMap / podMaps decisions in record order (node.go:131,149; scheduler.go:239-243,261-264)
+  std::vector<ApplyOp> dev; dev.reserve((size_t)n);
+  auto push = [&](const egs_mutation &m, int cancel) {
+    ApplyOp o; memset(&o, 0, sizeof o);
+    o.node = m.node_id; o.cancel = cancel; o.req = make_req(m.n_containers, m.units);
+    for (int c = 0; c < m.n_containers; c++) { o.n_idx[c] = m.n_idx[c]; for (int j = 0; j < m.n_idx[c]; j++) o.idx[c][j] = m.idx[c][j]; }
+    dev.push_back(o);
+  };
+  for (int i = 0; i < n; i++) {
+    const egs_mutation &m = ops[i];
+    if (m.kind == EGS_MUT_ADD) {
+      if (in_pod_maps(h, m.uid)) continue;
+      if (!in_pods_map(h, m.node_id, m.uid)) { push(m, 0); h->pods_map.insert(NodeUid{m.node_id, m.uid}); }
+      h->pod_maps.insert(m.uid);
+    } else if (m.kind == EGS_MUT_REPLAY) {
+      if (!in_pods_map(h, m.node_id, m.uid)) { push(m, 0); h->pods_map.insert(NodeUid{m.node_id, m.uid}); }
+    } else {
+      if (m.node_id >= 0 && in_pods_map(h, m.node_id, m.uid)) {
+        push(m, 1);
+        if (!h->pods_map.erase(NodeUid{m.node_id, m.uid})) h->auto_gone_node.insert(NodeUid{m.node_id, m.uid});
+      }
+      if (in_pod_maps(h, m.uid)) {
+        if (!h->pod_maps.erase(m.uid)) h->auto_gone_pod.insert(m.uid);
+        h->released.insert(m.uid);
+      }
+    }
+  }
+  if (dev.empty()) return EGS_OK;
+  // group by node, record order kept inside a node
+  std::vector<int> order(dev.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return dev[x].node < dev[y].node; });
+  const size_t nd = dev.size();
+  TRY(ensure_stage(h, nd * sizeof(ApplyOp) + (nd + 1) * sizeof(int32_t)));
+  CK(h, cudaStreamSynchronize(h->stream));
+  ApplyOp *so = (ApplyOp *)h->h_stage; int32_t *sg = (int32_t *)(so + nd);
+  int ng = 0;
+  for (size_t i = 0; i < nd; i++) {
+    so[i] = dev[order[i]];
+    if (i == 0 || so[i].node != so[i - 1].node) sg[ng++] = (int32_t)i;
+  }
+  sg[ng] = (int32_t)nd;
+  if (nd > h->ops_cap) {
+    if (h->d_ops) { cudaFree(h->d_ops); cudaFree(h->d_group_off); h->d_ops = nullptr; h->d_group_off = nullptr; h->ops_cap = 0; }
+    const size_t cap = std::max(nd, (size_t)1024);
+    CK(h, cudaMalloc(&h->d_ops, cap * sizeof(ApplyOp)));
+    CK(h, cudaMalloc(&h->d_group_off, (cap + 1) * sizeof(int32_t)));
+    h->ops_cap = cap;
+  }
+  CK(h, cudaMemcpyAsync(h->d_ops, so, nd * sizeof(ApplyOp), cudaMemcpyHostToDevice, h->stream));
+  CK(h, cudaMemcpyAsync(h->d_group_off, sg, (size_t)(ng + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  ApplyManyArgs ka;
+  ka.core = h->d_core; ka.mem = h->d_mem; ka.mem_total = h->d_mem_total; ka.ops = h->d_ops; ka.group_off = h->d_group_off; ka.n_groups = ng;
+  ka.all_st = h->d_st; ka.slot_stride = (size_t)h->n_pad; ka.n_slots = (int)h->shapes.size();
+  k_apply_many<<<(ng + 127) / 128, 128, 0, h->stream>>>(ka);
+  CK(h, cudaGetLastError());
+  return EGS_OK;
+}
+
+extern "C" int egs_mutations_apply(egs_handle *h, int n, const egs_mutation *ops) {
+  if (!h) return EGS_ERR_BAD_ARG;
+  Guard g(h);
+  TRY(flush_pending(h));
+  return mutations_apply_locked(h, n, ops);
+}
+
 extern "C" int egs_pod_known(egs_handle *h, uint64_t uid) {
   if (!h) return 0;
   Guard g(h);
@@ -851,6 +936,40 @@ extern "C" int egs_schedule_batch(egs_handle *h, int mode, int n_pods, const int
   PodOut o; o.node = out_node; o.status = out_status; o.alloc = out_alloc_mask; o.fit_count = out_fit_count;
   o.fit_digest = (unsigned long long *)out_fit_digest; o.score_digest = (unsigned long long *)out_score_digest;
   return batch_common(h, mode, n_pods, c_off, units, uids, o, false);
+}
+
+extern "C" int egs_schedule_batch_mut(egs_handle *h, int mode, int n_pods, const int32_t *c_off, const egs_unit *units,
+                                      const uint64_t *uids, int n_mut, const int32_t *mut_at, const egs_mutation *muts,
+                                      int32_t *out_node, int32_t *out_status, uint8_t *out_alloc_mask,
+                                      int32_t *out_fit_count, uint64_t *out_fit_digest, uint64_t *out_score_digest) {
+  if (!h || n_pods < 0 || n_mut < 0 || (n_mut > 0 && (!mut_at || !muts)) || (n_pods > 0 && (!c_off || !units))) return EGS_ERR_BAD_ARG;
+  for (int j = 0; j < n_mut; j++)
+    if (mut_at[j] < 0 || mut_at[j] > n_pods || (j > 0 && mut_at[j] < mut_at[j - 1])) return EGS_ERR_BAD_ARG;
+  Guard g(h);
+  // segments of pods between mutation points; the lock is held throughout, exactly one "call at a time"
+  int p = 0, j = 0;
+  while (p < n_pods || j < n_mut) {
+    int j1 = j;
+    while (j1 < n_mut && mut_at[j1] == p) j1++;
+    if (j1 > j) {
+      TRY(flush_pending(h));
+      TRY(mutations_apply_locked(h, j1 - j, muts + j));
+      j = j1;
+    }
+    if (p >= n_pods) break;
+    const int q = j < n_mut ? mut_at[j] : n_pods;                // next mutation point (> p)
+    PodOut o;
+    o.node = out_node ? out_node + p : nullptr; o.status = out_status ? out_status + p : nullptr;
+    o.alloc = out_alloc_mask ? out_alloc_mask + (size_t)p * EGS_C : nullptr; o.fit_count = out_fit_count ? out_fit_count + p : nullptr;
+    o.fit_digest = out_fit_digest ? (unsigned long long *)out_fit_digest + p : nullptr;
+    o.score_digest = out_score_digest ? (unsigned long long *)out_score_digest + p : nullptr;
+    // the segment's pods as a batch of its own: offsets rebased
+    std::vector<int32_t> off((size_t)(q - p) + 1);
+    for (int i = p; i <= q; i++) off[(size_t)(i - p)] = c_off[i] - c_off[p];
+    TRY(batch_common(h, mode, q - p, off.data(), units + c_off[p], uids ? uids + p : nullptr, o, false));
+    p = q;
+  }
+  return EGS_OK;
 }
 
 extern "C" int egs_schedule_batch_vec(egs_handle *h, int n_pods, const int32_t *c_off, const egs_unit *units,

@@ -321,6 +321,45 @@ __global__ void k_apply(ApplyArgs a) {
   memo_reset(a.all_st, a.slot_stride, a.n_slots, (size_t)a.node);
 }
 
+// Many AddPod / ForgetPod row updates in ONE launch: the host has grouped the records by node (record order kept
+// inside a node); one thread per touched node applies its run with the arithmetic of k_apply.
+struct ApplyOp { int node, cancel; Req req; int n_idx[EGS_C]; int8_t idx[EGS_C][EGS_G]; };
+struct ApplyManyArgs {
+  int32_t *core, *mem; const int32_t *mem_total;
+  const ApplyOp *ops; const int32_t *group_off; int n_groups;   // group g = ops[group_off[g] .. group_off[g+1])
+  uint8_t *all_st; size_t slot_stride; int n_slots;
+};
+__global__ void k_apply_many(ApplyManyArgs a) {
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= a.n_groups) return;
+  const int node = a.ops[a.group_off[gi]].node;
+  int32_t *c = a.core + (size_t)node * EGS_G, *m = a.mem + (size_t)node * EGS_G;
+  const int mt = a.mem_total[node];
+  for (int o = a.group_off[gi]; o < a.group_off[gi + 1]; o++) {
+    const ApplyOp &op = a.ops[o];
+    bool stop = false;
+    for (int i = 0; i < op.req.C && !stop; i++) {
+      const bool whole = op.req.cnt[i] > 0;
+      const int lim = whole ? op.n_idx[i] : (op.n_idx[i] > 0 ? 1 : 0);
+      for (int j = 0; j < lim; j++) {
+        const int g = op.idx[i][j];
+        if (op.cancel) {                                         // GPU.Sub gpu.go:41-49
+          if (whole) { c[g] = EGS_CORE_PER_GPU; m[g] = mt; } else { c[g] += op.req.core[i]; m[g] += op.req.mem[i]; }
+        } else {                                                 // CanAllocate + Add; first failure stops, no rollback (gpu.go:153-175)
+          if (whole) {
+            if (!(c[g] == EGS_CORE_PER_GPU && m[g] == mt)) { stop = true; break; }
+            c[g] = 0; m[g] = 0;
+          } else {
+            if (!(c[g] >= op.req.core[i] && m[g] >= op.req.mem[i])) { stop = true; break; }
+            c[g] -= op.req.core[i]; m[g] -= op.req.mem[i];
+          }
+        }
+      }
+    }
+  }
+  memo_reset(a.all_st, a.slot_stride, a.n_slots, (size_t)node);
+}
+
 // Rows of nodes [node0, node0+n) were overwritten from the host.  full != 0 (node_set: a fresh
 // NodeAllocator, node.go:42-50) drops every option; full == 0 (state_load) only clears the UNFIT
 // memos -- cached options stay, stale, exactly like the reference's map would.

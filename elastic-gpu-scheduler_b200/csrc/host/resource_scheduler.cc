@@ -2,6 +2,7 @@
 // C++ twin of the cgo shim shown in INTEGRATION.md.
 #include "resource_scheduler.h"
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
@@ -43,12 +44,12 @@ std::string CudaUnitScheduler::RequestString(const std::vector<egs_unit> &req) {
   return os.str();
 }
 
+// The pod UID crosses the C ABI as its 64-bit FNV-1a hash (as in integration/cuda_scheduler.go): no table that
+// grows with every pod ever seen and needs cleaning on ForgetPod.
 uint64_t CudaUnitScheduler::uidOf(const std::string &uid) {
-  auto it = uids_.find(uid);
-  if (it != uids_.end()) return it->second;
-  uint64_t v = uids_.size() + 1;
-  uids_.emplace(uid, v);
-  return v;
+  uint64_t h = 0xcbf29ce484222325ull;
+  for (unsigned char c : uid) { h ^= c; h *= 0x100000001b3ull; }
+  return h;
 }
 
 void CudaUnitScheduler::optionFromPod(const Pod &pod, std::vector<int32_t> *off, std::vector<int32_t> *idx) {
@@ -86,7 +87,12 @@ int CudaUnitScheduler::getNodeInfo(const std::string &name, std::string *err) {
   node_ids_.emplace(name, id);
   for (const auto &p : info.assumed_pods) {                                                    // node.go:52-54: na.Add(&pods[i], nil)
     std::vector<egs_unit> req;
-    if (!RequestOf(p, &req)) continue;
+    if (!RequestOf(p, &req)) {                   // not representable on the device path: say so, loudly -- the node's rows
+      fprintf(stderr, "libegs: assumed pod %s/%s on node %s has more than %d containers (or an out-of-range request): "   // would
+              "its GPU share is NOT subtracted from the node cache\n", p.ns.c_str(), p.name.c_str(), name.c_str(), EGS_MAX_CONTAINERS);  // otherwise be silently wrong
+      unsupported_.push_back(p.ns + "/" + p.name);
+      continue;
+    }
     std::vector<int32_t> off, idx;
     optionFromPod(p, &off, &idx);
     egs_node_replay_pod(h_, id, (int)req.size(), req.data(), off.data(), idx.data(), uidOf(p.uid));
@@ -182,7 +188,10 @@ std::string CudaUnitScheduler::AddPod(const Pod &pod) {
   int id = getNodeInfo(pod.node_name, &err);
   if (id < 0) return err;
   std::vector<egs_unit> req;
-  if (!RequestOf(pod, &req)) return "";
+  if (!RequestOf(pod, &req)) {                 // never drop silently: the caller (controller.go:330) logs the error
+    unsupported_.push_back(pod.ns + "/" + pod.name);
+    return "libegs: pod " + pod.ns + "/" + pod.name + " has more than 4 containers (or an out-of-range request): not accounted on the device path";
+  }
   std::vector<int32_t> off, idx;
   optionFromPod(pod, &off, &idx);
   egs_pod_apply(h_, id, (int)req.size(), req.data(), off.data(), idx.data(), uidOf(pod.uid));  // error discarded, scheduler.go:242

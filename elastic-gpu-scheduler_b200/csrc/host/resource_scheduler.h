@@ -80,7 +80,7 @@ class CudaUnitScheduler : public ResourceScheduler {
 
  private:
   int getNodeInfo(const std::string &name, std::string *err);   // scheduler.go:62-84 -> dense id or -1
-  uint64_t uidOf(const std::string &uid);
+  static uint64_t uidOf(const std::string &uid);
   std::string gpusJson(int node_id);                            // GPUs.String (gpu.go:60-63)
   static void optionFromPod(const Pod &pod, std::vector<int32_t> *off, std::vector<int32_t> *idx);  // allocate.go:75-93
 
@@ -89,7 +89,7 @@ class CudaUnitScheduler : public ResourceScheduler {
   NodeProvider provider_;
   std::unordered_map<std::string, int> node_ids_;
   std::vector<std::string> node_names_;
-  std::unordered_map<std::string, uint64_t> uids_;
+  std::vector<std::string> unsupported_;          // pods the device path could not account (reported, never dropped silently)
 };
 
 }  // namespace egs

@@ -136,6 +136,31 @@ int egs_node_replay_pod(egs_handle *h, int node_id, int n_containers, const egs_
 /* ForgetPod (scheduler.go:247-267 -> node.go:129-140 -> gpu.go:177-191); node_id < 0 == empty NodeName. */
 int egs_pod_cancel(egs_handle *h, int node_id, int n_containers, const egs_unit *units,
                    const int32_t *alloc_off, const int32_t *alloc_idx, uint64_t uid);
+/* ---- mutation stream (controller.go:154-185,301-331: AddPod / ForgetPod arrive between scheduling verbs, under the
+ * same lock) and bulk start-up replay (scheduler.go:86-106, node.go:52-54) ---------------------------------------- */
+enum egs_mutation_kind { EGS_MUT_ADD = 0,      /* AddPod     == egs_pod_apply       */
+                         EGS_MUT_FORGET = 1,   /* ForgetPod  == egs_pod_cancel (node_id < 0: empty NodeName) */
+                         EGS_MUT_REPLAY = 2 }; /* NodeAllocator.Add at node load == egs_node_replay_pod */
+typedef struct egs_mutation {
+  int32_t kind, node_id, n_containers, pad;
+  egs_unit units[EGS_MAX_CONTAINERS];
+  int8_t n_idx[EGS_MAX_CONTAINERS];                     /* GPU indices of container c in annotation order ...      */
+  int8_t idx[EGS_MAX_CONTAINERS][EGS_MAX_GPUS];         /* ... idx[c][0 .. n_idx[c])                                */
+  uint64_t uid;
+} egs_mutation;
+/* Applies the records IN ORDER -- observably identical to issuing the single-pod verbs one by one -- with ONE kernel
+ * launch: the podsMap / podMaps decisions are taken on the host in record order, the surviving row updates are grouped
+ * by node (order kept inside a node) and one thread per touched node applies them.  10^5 assumed pods replay in one
+ * launch.  Returns the first record's error (nothing applied) when a record is malformed. */
+int egs_mutations_apply(egs_handle *h, int n, const egs_mutation *ops);
+/* egs_schedule_batch with a mutation stream woven in: record j is applied right before pod mut_at[j] (mut_at ascending,
+ * 0 <= mut_at[j] <= n_pods; equal positions keep record order) -- the interleaving the reference's single lock produces
+ * when the informer delivers AddPod / ForgetPod between two scheduling cycles.  Outputs as egs_schedule_batch. */
+int egs_schedule_batch_mut(egs_handle *h, int mode, int n_pods, const int32_t *c_off, const egs_unit *units,
+                           const uint64_t *uids, int n_mut, const int32_t *mut_at, const egs_mutation *muts,
+                           int32_t *out_node, int32_t *out_status, uint8_t *out_alloc_mask,
+                           int32_t *out_fit_count, uint64_t *out_fit_digest, uint64_t *out_score_digest);
+
 int egs_pod_known(egs_handle *h, uint64_t uid);      /* 1 / 0, scheduler.go:269-274 */
 int egs_pod_released(egs_handle *h, uint64_t uid);   /* 1 / 0, scheduler.go:276-281 */
 
