@@ -26,7 +26,7 @@ SYMBOLS = [
     "egs_state_snapshot", "egs_state_restore",
     "egs_filter", "egs_score", "egs_bind", "egs_option_peek", "egs_option_dump", "egs_pod_apply", "egs_node_replay_pod", "egs_pod_cancel",
     "egs_mutations_apply", "egs_schedule_batch_mut", "egs_pod_known", "egs_pod_released", "egs_schedule_batch", "egs_schedule_batch_vec", "egs_schedule_batch_device",
-    "egs_shard_set", "egs_shard_range", "egs_comm_unique_id", "egs_comm_init", "egs_profile_evaluate", "egs_profile_get",
+    "egs_shard_set", "egs_shard_range", "egs_comm_unique_id", "egs_comm_init", "egs_comm_init_local", "egs_profile_evaluate", "egs_profile_get",
     "egs_profile_reset", "egs_get_stream", "egs_rounds_stats", "egs_mix64",
 ]
 
@@ -87,6 +87,7 @@ def load(build: bool = True):
     L.egs_shard_range.argtypes = [i32, i32, i32, C.POINTER(i32), C.POINTER(i32)]
     L.egs_comm_unique_id.argtypes = [vp]
     L.egs_comm_init.argtypes = [vp, vp]
+    L.egs_comm_init_local.argtypes = [vp, i32]
     L.egs_profile_evaluate.argtypes = [vp, i32, vp, i32, i32, C.POINTER(C.c_float)]
     L.egs_profile_get.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(C.c_double)]
     L.egs_profile_reset.argtypes = [vp, i32]
@@ -345,6 +346,14 @@ class Egs:
 
     def profile_reset(self, timing: bool = False):
         self._ck(self.L.egs_profile_reset(self.h, int(timing)), "egs_profile_reset")
+
+
+def comm_init_local(handles) -> None:
+    """In-process shard group over Egs objects (rank r = handles[r]); drive each handle from its own thread."""
+    arr = (C.c_void_p * len(handles))(*[h.h for h in handles])
+    st = load().egs_comm_init_local(arr, len(handles))
+    if st != EGS_OK:
+        raise EgsError(st, "egs_comm_init_local")
 
 
 def _one_nccl():

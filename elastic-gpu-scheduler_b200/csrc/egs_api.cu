@@ -1028,6 +1028,7 @@ extern "C" int egs_shard_set(egs_handle *h, int rank, int world) {
   return EGS_OK;
 }
 extern "C" int egs_comm_unique_id(uint8_t out_id[128]) { return rounds_comm_unique_id(out_id); }
+extern "C" int egs_comm_init_local(egs_handle **handles, int world) { return rounds_comm_init_local(handles, world); }
 extern "C" int egs_comm_init(egs_handle *h, const uint8_t id[128]) {
   if (!h || !id) return EGS_ERR_BAD_ARG;
   Guard g(h);

@@ -27,6 +27,10 @@
 // It is only valid while the node's rows stay unchanged; once a pod of that shape has run
 // ("observed"), it is an ordinary cached option (OPT_CACHED).
 #pragma once
+#include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <vector>
 #include "egs_kernels.cuh"
 
@@ -1448,8 +1452,29 @@ __global__ void k_clear_u8(uint8_t *p, int n) {
 // ---------------------------------------------------------------------------------------------
 struct egs_handle;
 
+// In-process shard group (several handles, one per shard, in ONE process; typically all on one device): the
+// per-round exchange is a device-to-device copy of every peer's candidate buffer ordered by CUDA events, with a host
+// barrier between the threads that drive the handles.  Same data path as the NCCL exchange; lets a single-GPU box
+// run (and test) the sharded engine at world sizes 2..8.
+struct LocalGroup {
+  int world = 0;
+  std::vector<egs_handle *> members;
+  std::mutex mu; std::condition_variable cv; int arrived = 0; long long generation = 0;
+  bool broken = false;
+  bool barrier() {                                   // false: a member never came (its batch failed): the group is broken
+    std::unique_lock<std::mutex> lk(mu);
+    if (broken) return false;
+    const long long g = generation;
+    if (++arrived == world) { arrived = 0; generation++; cv.notify_all(); return true; }
+    if (!cv.wait_for(lk, std::chrono::seconds(60), [&] { return generation != g || broken; })) { broken = true; cv.notify_all(); }
+    return !broken;
+  }
+};
+
 struct RoundsState {
   void *comm = nullptr;             // ncclComm_t
+  std::shared_ptr<LocalGroup> local;                    // in-process shard group (instead of NCCL)
+  cudaEvent_t ev_ready = nullptr, ev_copied = nullptr;   // own buffer written / peers' buffers copied
   uint8_t *d_pod_sidx = nullptr; int pod_cap = 0;
   uint8_t *d_obs = nullptr; int obs_cap = 0;
   unsigned long long *d_cta_lists = nullptr; AggPart *d_cta_agg = nullptr; int grid = 0, cta_nsc = 0;
@@ -1467,3 +1492,4 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
 static void rounds_free(RoundsState *r);
 static int rounds_comm_unique_id(uint8_t out_id[128]);
 static int rounds_comm_init(egs_handle *h, const uint8_t id[128]);
+static int rounds_comm_init_local(egs_handle **handles, int world);

@@ -44,6 +44,8 @@ static void rounds_free(RoundsState *r) {
   if (r->comm && nccl_api()) nccl_api()->CommDestroy((ncclComm_t)r->comm);
   void *dev[] = {r->d_pod_sidx, r->d_obs, r->d_cta_lists, r->d_cta_agg, r->d_bufs, r->d_rd, r->d_ctl};
   for (void *p : dev) if (p) cudaFree(p);
+  if (r->ev_ready) cudaEventDestroy(r->ev_ready);
+  if (r->ev_copied) cudaEventDestroy(r->ev_copied);
   if (r->h_rd) cudaFreeHost(r->h_rd);
   if (r->h_ctl) cudaFreeHost(r->h_ctl);
   *r = RoundsState();
@@ -68,6 +70,29 @@ static int rounds_comm_init(egs_handle *h, const uint8_t id[128]) {
   return EGS_OK;
 }
 
+
+// In-process shard group over `world` handles (rank r = handles[r], each already egs_shard_set(r, world)).
+static int rounds_comm_init_local(egs_handle **handles, int world) {
+  if (!handles || world < 2 || world > RD) return EGS_ERR_BAD_ARG;
+  auto G = std::make_shared<LocalGroup>();
+  G->world = world;
+  for (int r = 0; r < world; r++) {
+    egs_handle *h = handles[r];
+    if (!h || h->world != world || h->rank != r) return EGS_ERR_BAD_ARG;
+    G->members.push_back(h);
+  }
+  for (int r = 0; r < world; r++) {
+    egs_handle *h = handles[r];
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);
+    if (!h->rounds.ev_ready) {
+      CK(h, cudaEventCreateWithFlags(&h->rounds.ev_ready, cudaEventDisableTiming));
+      CK(h, cudaEventCreateWithFlags(&h->rounds.ev_copied, cudaEventDisableTiming));
+    }
+    h->rounds.local = G;
+  }
+  return EGS_OK;
+}
 
 // ---- resolver configuration by the size of the round's shape set
 struct MwConfig { int inst; int nt; int rkm; size_t smem_struct; };
@@ -139,7 +164,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   (void)c_off; (void)units;
   RoundsState &R = h->rounds;
   *n_done = 0;
-  if (h->world > 1 && !R.comm) return fail(h, EGS_ERR_COMM, "sharded handle without egs_comm_init");
+  if (h->world > 1 && !R.comm && !R.local) return fail(h, EGS_ERR_COMM, "sharded handle without egs_comm_init");
   if (h->world > RD) return fail(h, EGS_ERR_BAD_ARG, "too many shards");
 
   // distinct shapes of the whole batch, in order of first appearance: when they fit one round set the set
@@ -227,12 +252,30 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   ra.p0 = -1; ra.p_limit = 0; ra.out = out; ra.ctl = R.d_ctl; ra.rke = rke; ra.nw = nw; ra.use_hpay = use_hpay; ra.use_lmax = use_lmax;
 
   int ns_round = ns_cfg;                                        // grid of k_merge
+  bool local_copied = false;
   auto launch_round = [&]() -> int {
     if (h->timing) CK(h, cudaEventRecord(ev[0], h->stream));
     k_select<<<grid, SEL_THREADS, 0, h->stream>>>(sa);
     if (h->timing) CK(h, cudaEventRecord(ev[1], h->stream));
+    if (local_copied)                                           // peers must have copied my previous buffer before k_merge rewrites it
+      for (egs_handle *peer : R.local->members) if (peer != h) CK(h, cudaStreamWaitEvent(h->stream, peer->rounds.ev_copied, 0));
     k_merge<<<ns_round, 256, 0, h->stream>>>(ma);
-    if (h->world > 1)
+    if (h->world > 1 && R.local) {
+      // in-process group: wait until no peer still reads my buffer of the previous round (enqueued BEFORE k_merge
+      // overwrote it, see below), publish mine, copy theirs
+      LocalGroup &G = *R.local;
+      CK(h, cudaEventRecord(R.ev_ready, h->stream));
+      if (!G.barrier()) return fail(h, EGS_ERR_COMM, "in-process shard group: a member did not arrive");   // all recorded ev_ready
+      for (egs_handle *peer : G.members) {
+        if (peer == h) continue;
+        CK(h, cudaStreamWaitEvent(h->stream, peer->rounds.ev_ready, 0));
+        CK(h, cudaMemcpyAsync(R.d_bufs + (size_t)peer->rank * L.bytes, peer->rounds.d_bufs + (size_t)peer->rank * L.bytes,
+                              (size_t)L.bytes, cudaMemcpyDeviceToDevice, h->stream));
+      }
+      CK(h, cudaEventRecord(R.ev_copied, h->stream));
+      if (!G.barrier()) return fail(h, EGS_ERR_COMM, "in-process shard group: a member did not arrive");   // all recorded ev_copied
+      local_copied = true;
+    } else if (h->world > 1)
       NCK(h, nccl_api()->AllGather(R.d_bufs + (size_t)h->rank * L.bytes, R.d_bufs, (size_t)L.bytes, ncclChar, (ncclComm_t)R.comm, h->stream));
     if (h->timing) CK(h, cudaEventRecord(ev[2], h->stream));
     if (engine_tw) {                                            // one ticket warp + nw helper warps

@@ -232,6 +232,11 @@ int egs_shard_set(egs_handle *h, int rank, int world);
 int egs_shard_range(int max_nodes, int rank, int world, int *lo, int *hi);
 int egs_comm_unique_id(uint8_t out_id[128]);
 int egs_comm_init(egs_handle *h, const uint8_t id[128]);
+/* In-process shard group instead of NCCL: handles[r] is rank r of `world` (each after egs_shard_set(r, world)), all in
+ * this process -- on one device or several.  The per-round exchange becomes device-to-device copies ordered by CUDA
+ * events; each handle's batch call must then be issued from its own thread, all `world` of them concurrently (they
+ * rendezvous once per round).  Same kernels and buffers as the NCCL path: a single-GPU box can run the sharded engine. */
+int egs_comm_init_local(egs_handle **handles, int world);
 
 /* ---- instrumentation --------------------------------------------------------- */
 

@@ -90,3 +90,53 @@ def test_nccl_sharded_rounds_equal_unsharded():
                         "--master-addr", "127.0.0.1", "--master-port", "29731",
                         os.path.join(ROOT, "tools", "multi_gpu_check.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "MULTI_GPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_engine_in_process_equals_unsharded(world):
+    """The sharded rounds engine at world sizes 2 / 4 / 8 on whatever GPUs exist (all shards on device 0 of a
+    single-GPU box): an in-process shard group (egs_comm_init_local) replaces NCCL by device-to-device copies of the
+    same candidate buffers; kernels, buffers and the replicated resolver are those of the NCCL path.  Every rank's
+    outputs must equal the unsharded run bit for bit, and every shard's rows the unsharded rows."""
+    import threading
+    import egs_b200
+    cap = egs_b200.capi
+    F = ["node", "status", "alloc_mask", "fit_count", "fit_digest", "score_digest"]
+    cases = [(4, None, 30000, None), (1, None, None, None), (2, 3000, 6000, None), (3, 300, 2000, 0), (4, 1000, 3000, 0)]
+    for cfg, nn, npods, pol in cases:
+        w = egs_b200.workloads.config(cfg, n_nodes=nn, n_pods=npods, policy=pol)
+        e0 = egs_b200.Egs(w.policy, w.n_nodes)
+        e0.state_load_bulk(0, w.gpus, w.mem_total, w.core, w.mem)
+        ref = e0.schedule_batch(w.c_off, w.units, mode=cap.EGS_MODE_ROUNDS)
+        ref_core, ref_mem, _, _ = e0.state_dump()
+        e0.close()
+        hs = []
+        for r in range(world):
+            e = egs_b200.Egs(w.policy, w.n_nodes)
+            e.shard_set(r, world)
+            hs.append(e)
+        cap.comm_init_local(hs)
+        for e in hs:
+            e.state_load_bulk(0, w.gpus, w.mem_total, w.core, w.mem)
+        outs, errs = [None] * world, []
+
+        def run(r):
+            try:
+                outs[r] = hs[r].schedule_batch(w.c_off, w.units, mode=cap.EGS_MODE_ROUNDS)
+            except Exception as ex:   # pragma: no cover
+                errs.append(repr(ex))
+        th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join(timeout=600)
+        assert not errs, errs
+        for r in range(world):
+            for f in F:
+                assert np.array_equal(ref[f], outs[r][f]), f"cfg{cfg} world {world} rank {r}: {f} differs"
+            lo, hi = cap.shard_range(w.n_nodes, r, world)
+            core, mem, _, _ = hs[r].state_dump(lo, hi - lo)
+            assert np.array_equal(core, ref_core[lo:hi]) and np.array_equal(mem, ref_mem[lo:hi]), f"rows of shard {r}"
+        for e in hs:
+            e.close()
