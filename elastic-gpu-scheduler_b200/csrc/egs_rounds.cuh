@@ -15,13 +15,14 @@
 //   k_resolve_mw (ONE CTA, one OWNER WARP per request shape, shared-memory resident): replays the
 //             pods in order.  The pods of one shape form a chain that only touches other shapes
 //             through the rows of the nodes it binds, so every owner warp prepares its next pod
-//             (best tracked option of its shape) on its own and the warps then pass a TICKET in
-//             pod order: inside the ticket the pod's pending option is Traded on the current
-//             rows, the winner = max(tracked options, best untracked list head) is bound
-//             (Transact on the shared-memory copy of the node) and the ticket moves on; outputs,
-//             digests and the owner's private tables are updated after the ticket was released.
-//             Stops early when a list runs dry or the tracked table is full; writes the tracked
-//             nodes back.
+//             on its own (best tracked option of its shape, its candidate lists, payload prefetch,
+//             a speculative Trade of the pending option under the rows' seqlock) and the warps then
+//             pass a TICKET in pod order (mbarrier): inside the ticket the speculative Trade is
+//             validated (97 % hold) or redone on the current rows, the winner = max(tracked options,
+//             best untracked list head) is bound (Transact on the shared-memory copy of the node) and
+//             the ticket moves on; outputs, digests and the owner's private tables are updated after
+//             the ticket was released.  Stops early when a list runs dry or the tracked table is
+//             full; writes the tracked nodes back.
 //
 // Option states: OPT_NEW marks an option select evaluated AHEAD of the shape's next filter.
 // It is only valid while the node's rows stay unchanged; once a pod of that shape has run
@@ -394,7 +395,6 @@ struct MwArgs {
   int rke;                          // list entries per (shape, shard) held in shared memory
   int nw;                           // worker warps
   int use_hpay;                     // shared memory holds one prefetched candidate payload per shape
-  int use_lmax;                     // shared memory holds the per-lane column maxima of tkey per shape
 };
 
 template <int NS, int NT>
@@ -409,11 +409,6 @@ struct MwSmem {
   uint32_t al[NS][NT];               // option.Allocated masks
   unsigned pmask[NS][NT / 32];       // tracked slots whose option is ABSENT: Trade at the shape's next pod
   int afit[NS], bh_d[NS], dry[NS], observed[NS], xbest_t[NS], hv_nT[NS], hpay_node[NS];
-  int lm_seen[NS];                   // lmax[s] covers the slots [0, lm_seen[s]); -1: to be rebuilt
-  // ticket-warp engine: per shape, pods the ticket warp has finished / pods the helper has digested (+ prepared the next)
-  int seq_done[NS], seq_ready[NS];
-  alignas(16) int pkg[NS][16];       // helper -> ticket warp: what the next pod of the shape needs (see PK_*)
-  alignas(16) int evt[NS][8];        // ticket warp -> helper: what the last pod of the shape did (see EV_*)
   int pu[NS];                        // summary of pmask[s]: -1 none, t >= 0 exactly slot t, -2 unknown / several
   int rq_single[NS], rq_core[NS], rq_mem[NS]; uint32_t rq_cmask[NS];
   uint8_t st[NS][NT];                // OPT_*
@@ -430,18 +425,13 @@ struct MwSmem {
   int stop, stop_reason, stop_p, nT, n_observed, mono, p0, p_end;
 };
 #define MW_STOP 0x40000000
-#ifndef MW_POLL
-#define MW_POLL 0
-#endif
-#define MW_LA 3                            // an owner is woken (mbarrier) when the ticket is MW_LA pods before its pod
 
-// Ticket hand-over in two levels.  (1) `turn` in shared memory: the holder of pod p's ticket stores p+1 after its last
-// row store (same lane, program order; shared memory is one in-order unit per SM) and the owner of p+1 sees it on
-// its next poll -- no fence and no release/acquire instruction on the critical path.  (2) Only the owners of the
-// next MW_LA pods poll; everybody further away sleeps in hardware on its own mbarrier (try_wait suspends the
-// warp) and is woken by the owner of pod p - MW_LA right after that one handed its ticket on, i.e. by a warp that
-// is no longer on the critical path.  Polling by 16 warps steals issue slots from the ticket holder; an mbarrier
-// arrive with release semantics on the critical path costs several hundred cycles -- both measured.
+// Ticket hand-over: `turn` in shared memory names the pod whose ticket is open (bookkeeping, and the stop signal);
+// the owner of the next pod SLEEPS in hardware on its own mbarrier (try_wait suspends the warp) and is woken by ONE
+// arrive of the warp that finished the previous pod.  Measured alternatives (tools/micro/handoff_bench.cu and A/B runs
+// of this kernel): every warp polling one word steals issue slots from the ticket holder (-25 %); a two-level scheme
+// (only the next owners poll, the others sleep) was 10 % slower than this; a bare hand-over costs ~300 cycles
+// whatever the mechanism.
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
 }
@@ -456,11 +446,6 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, unsigned 
 }
 __device__ __forceinline__ int ld_vol(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 __device__ __forceinline__ void st_vol(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
-__device__ __forceinline__ int4 ld_vol4(const int *p) {         // 16-byte volatile load from shared memory
-  int4 v;
-  asm volatile("ld.volatile.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
-  return v;
-}
 
 template <class SM>
 __device__ __forceinline__ unsigned hset_slot(uint32_t node) {
@@ -599,7 +584,7 @@ __device__ __noinline__ int general_pod(SM &S, const MwArgs &a, const unsigned l
   if (nT >= SM::HS / 2) return 2;                               // no free tracked slot for a new winner
   maintain_heads(S, lk, a.n_shards, a.rke, s, lane, true);      // inside the ticket the tracked set is exact
   if (S.dry[s]) return 3;                                       // a truncated list ran dry: next round
-  if (lane == 0) { S.xbest[s] = 0; S.xbest_t[s] = -1; S.lm_seen[s] = -1; }   // the scan below sees every slot; column maxima are rebuilt later
+  if (lane == 0) { S.xbest[s] = 0; S.xbest_t[s] = -1; }         // the scan below sees every slot
   if (!S.observed[s]) {                                         // first pod of this shape in the round:
     for (int t = lane; t < nT; t += 32) if (S.st[s][t] == OPT_NEW) S.st[s][t] = OPT_CACHED;   // NEW options are now ordinary
     __syncwarp();
@@ -746,7 +731,6 @@ __device__ __noinline__ int general_pod(SM &S, const MwArgs &a, const unsigned l
           S.st[s2][t] = OPT_ABSENT; S.tkey[s2][t] = 0; S.pmask[s2][t >> 5] |= pbit; S.pu[s2] = -2;
           S.afit[s2] -= 1; S.afd[s2] -= S.fterm[t]; S.asd[s2] -= score_term_b(S.sbase[t], key_score(k2));
           if (S.xbest_t[s2] == t) { S.xbest[s2] = 0; S.xbest_t[s2] = -1; }   // (an unobserved shape rescans anyway)
-          S.lm_seen[s2] = -1;
         }
       }
     }
@@ -800,10 +784,6 @@ __device__ __noinline__ bool resolve_prologue(SM &S, const MwArgs &a, unsigned l
     }
     S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd; S.observed[s] = 0; S.pu[s] = -1;
     S.xbest[s] = 0; S.xbest_t[s] = -1; S.hv_nT[s] = -1; S.hpay_node[s] = -1; S.bh[s] = 0; S.bh_d[s] = 0; S.dry[s] = 0;
-    S.lm_seen[s] = -1;
-    S.seq_done[s] = 0; S.seq_ready[s] = 0;
-    for (int i = 0; i < 16; i++) S.pkg[s][i] = 0;
-    S.pkg[s][10] = 1;                                             // PK_MODE: the first pod of a shape in a round is a general pod
     if (s < ns) {
       S.reqs[s] = a.rd->reqs[s];
       const Req &r = a.rd->reqs[s];
@@ -884,9 +864,6 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
   const int ns = a.rd->ns;
   unsigned long long *lk = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15));   // [ns][D][rke]
   char *hpay = a.use_hpay ? reinterpret_cast<char *>(lk + (size_t)ns * D * rke) : nullptr;                        // [ns][cand_bytes]
-  // column maxima of tkey: lane L keeps max over the slots t = L (mod 32) of its shapes -> the owner's scan is 1 load
-  unsigned long long *lmax = a.use_lmax ? reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15) + (size_t)ns * D * rke * 8 + (a.use_hpay ? (size_t)ns * a.L.cand_bytes : 0)) : nullptr;   // [ns][32]
-  int *lmax_t = lmax ? reinterpret_cast<int *>(lmax + (size_t)ns * 32) : nullptr;                                 // [ns][32]
   if (!resolve_prologue(S, a, lk)) return;
   const int p0 = S.p0, p_end = S.p_end;
 #ifdef EGS_RESOLVE_PROF
@@ -938,20 +915,9 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
           pm[j] &= ~(1u << l);
           p = cb + best_i;
           s = (__shfl_sync(0xffffffffu, myword, l) >> (8 * j)) & 0xFF;
-          // whom do I wake after my ticket (the owner of p + MW_LA, unless it is awake anyway: it owns one of the pods
-          // p .. p + MW_LA - 1), and do I sleep before polling (same rule seen from the other side)?
-#if MW_POLL
-          wake = owner_rel(best_i + MW_LA);
-          sleep_first = p - MW_LA >= p0;
-#pragma unroll
-          for (int k = 1; k <= MW_LA; k++) {
-            if (k < MW_LA && owner_rel(best_i + k) == wake) wake = -1;
-            if (owner_rel(best_i - k) == warp) sleep_first = false;
-          }
-#else
+          // whom do I wake after my ticket (the owner of p + 1 unless that is me), and do I sleep before mine?
           wake = owner_rel(best_i + 1);                           // the next owner sleeps on its mbarrier until I arrive
           sleep_first = p > p0 && owner_rel(best_i - 1) != warp;  // exactly one arrive per wait
-#endif
           if (wake == warp) wake = -1;
           break;
         }
@@ -989,15 +955,8 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
         const int pre_nT = ld_vol(&S.nT);
         __threadfence_block();
         unsigned long long b = 0; int bt = -1;
-        const int seen = lmax ? S.lm_seen[s] : -1;
-        if (seen < 0) {                                           // (re)build: lane L scans its column t = L, L+32, ...
 #pragma unroll 4
-          for (int t = lane; t < pre_nT; t += 32) { const unsigned long long k = S.tkey[s][t]; if (k > b) { b = k; bt = t; } }
-        } else {                                                  // cached column maxima + the slots installed since
-          b = lmax[s * 32 + lane]; bt = lmax_t[s * 32 + lane];
-          for (int t = seen + ((lane - seen) & 31); t < pre_nT; t += 32) { const unsigned long long k = S.tkey[s][t]; if (k > b) { b = k; bt = t; } }
-        }
-        if (lmax) { lmax[s * 32 + lane] = b; lmax_t[s * 32 + lane] = bt; if (lane == 0) S.lm_seen[s] = pre_nT; }
+        for (int t = lane; t < pre_nT; t += 32) { const unsigned long long k = S.tkey[s][t]; if (k > b) { b = k; bt = t; } }
         int owner;
         pre_best = warp_max_key_fwd(b, owner);
         pre_t = __shfl_sync(0xffffffffu, bt, owner);
@@ -1017,23 +976,11 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
       PROF_T(0)
       // ======== the ticket
       bool stopped = false;
-#if MW_POLL
-      if (sleep_first) {                                          // far from my turn: sleep until the ticket is MW_LA pods away
-        while (!mbar_try_wait(&S.mbar[warp], ph)) { if (ld_vol(&S.turn) & MW_STOP) { stopped = true; break; } }
-        ph ^= 1u;
-      }
-      while (!stopped) {
-        const int t = ld_vol(&S.turn);
-        if (t == p) break;
-        if (t & MW_STOP) stopped = true;
-      }
-#else
       if (sleep_first) {                                          // else: I still hold the ticket
         while (!mbar_try_wait(&S.mbar[warp], ph)) { if (ld_vol(&S.turn) & MW_STOP) { stopped = true; break; } }
         ph ^= 1u;
         if (ld_vol(&S.turn) & MW_STOP) stopped = true;
       }
-#endif
       if (stopped) break;
       PROF_T(1)
       int reason = 0;
@@ -1101,9 +1048,7 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
           if (lane == 0) {
             if (xb != 0) { S.xbest[s] = 0; S.xbest_t[s] = -1; }
             st_vol(&S.turn, p + 1);
-#if !MW_POLL
             if (wake >= 0) mbar_arrive(&S.mbar[wake]);
-#endif
           }
 #ifdef EGS_RESOLVE_PROF
           { const long long n_ = clock64(); prof[from_head && win != 0 ? 5 : 2] += n_ - tprev;
@@ -1111,9 +1056,6 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
             tprev = n_; }
 #endif
           PROF_C(6, 1)
-#if MW_POLL
-          if (lane == 0 && wake >= 0) mbar_arrive(&S.mbar[wake]);   // off the critical path
-#endif
           const int fit = afit + (bk >= 0);
           const unsigned long long fd = afd + (bk >= 0 ? ft_u : 0ull);
           const unsigned long long sd = asd + (bk >= 0 ? score_term_b(sb_u, sc) : 0ull);
@@ -1139,17 +1081,6 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
             if (a.out.alloc) reinterpret_cast<uint32_t *>(a.out.alloc)[p] = o_masks;
           }
           __syncwarp();
-          if (lmax) {                                             // the columns of the two entries that changed
-            const int seen = S.lm_seen[s];
-            const bool mine = (u >= 0 && u < seen && (u & 31) == lane) || (win != 0 && tw < seen && (tw & 31) == lane);
-            if (__any_sync(0xffffffffu, mine)) {
-              unsigned long long b = 0; int bt = -1;
-#pragma unroll 4
-              for (int t = lane; t < seen; t += 32) { const unsigned long long k = mine ? S.tkey[s][t] : 0ull; if (k > b) { b = k; bt = t; } }
-              if (mine) { lmax[s * 32 + lane] = b; lmax_t[s * 32 + lane] = bt; }
-            }
-            __syncwarp();
-          }
           PROF_T(3)
           continue;
         }
@@ -1172,266 +1103,6 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
   resolve_epilogue(S, a);
 #ifdef EGS_RESOLVE_PROF
   if (lane == 0 && warp < nw) for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)&a.ctl->prof[i], (unsigned long long)prof[i]);
-#endif
-}
-
-// --------------------------------------------------------------------------------------------
-// k_resolve_tw: ONE ticket warp + one helper warp per shape.
-//
-// Measured on the owner-warp engine above: a warp-to-warp hand-over costs ~300 cycles whatever the mechanism, and
-// the preparation / post-processing of an owner (~4000 cycles) stalls the chain whenever a shape recurs within a
-// few pods.  Here the ordered part of EVERY pod runs on one warp, back to back, with no hand-over; the helper of
-// shape s digests what the ticket warp did to the shape's last pod (option table, aggregates, per-pod outputs) and
-// prepares the next one (best tracked option, list heads, payload prefetch, speculative Trade of the pending
-// option under the rows' seqlock) while the ticket warp works on other shapes.  The ticket warp waits for a helper
-// only when the same shape comes again before its helper is done.
-//   pkg[s] (helper -> ticket warp)   evt[s] (ticket warp -> helper)   seq_ready[s] / seq_done[s] order them.
-// --------------------------------------------------------------------------------------------
-#define PK_BEST 0      // u64
-#define PK_HEAD 2      // u64
-#define PK_TKEY 4      // u64: cand_key of the speculative Trade (0: no fit)
-#define PK_BEST_T 6
-#define PK_U 7
-#define PK_VPRE 8      // seqlock value the speculative Trade saw (-1: none)
-#define PK_AL 9        // Allocated mask of the best tracked option
-#define PK_MODE 10     // 0 fast, 1 general
-#define PK_DRY 11
-#define PK_UND 12      // node id of slot u
-#define PK_BK 13       // folded key of the speculative Trade (-1: no fit)
-#define EV_WIN 0       // u64
-#define EV_P 2
-#define EV_U 3
-#define EV_BK 4
-#define EV_TW 5
-#define EV_FLAGS 6     // 1 from_head, 2 transact ok, 4 general pod (nothing to digest)
-#define EV_MASKS 7
-
-template <int NS, int NT>
-__global__ void __launch_bounds__(32 * (MW_MAX_WARPS + 1), 1) k_resolve_tw(MwArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  using SM = MwSmem<NS, NT>;
-  SM &S = *reinterpret_cast<SM *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int D = a.n_shards, rke = a.rke, nh = a.nw;              // helpers: warps 0..nh-1; ticket warp: warp nh (highest id)
-  const int ns = a.rd->ns;
-  unsigned long long *lk = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15));   // [ns][D][rke]
-  char *hpay = a.use_hpay ? reinterpret_cast<char *>(lk + (size_t)ns * D * rke) : nullptr;                        // [ns][cand_bytes]
-  if (!resolve_prologue(S, a, lk)) return;
-  const int p0 = S.p0, p_end = S.p_end;
-  const bool mono = S.mono != 0;
-  const int gl = lane & 7;
-#ifdef EGS_RESOLVE_PROF
-  long long prof[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long tprev = clock64();
-#endif
-  if (warp == nh) {
-    // =========================================================== the ticket warp
-    int cb = p0 & ~3;
-    uint32_t myword = 0xFFFFFFFFu;
-    auto load_chunk = [&](int base) {
-      const int q = base + 4 * lane;
-      myword = q < p_end ? *reinterpret_cast<const uint32_t *>(a.pod_sidx + q) : 0xFFFFFFFFu;
-    };
-    load_chunk(cb);
-    int reason = 0, p = p0;
-    for (; p < p_end; p++) {
-      if (p - cb >= 128) { cb += 128; load_chunk(cb); }
-      const int i = p - cb;
-      const int s = (int)((__shfl_sync(0xffffffffu, myword, i >> 2) >> (8 * (i & 3))) & 0xFFu);
-      const int k = S.seq_done[s];
-      while (ld_vol(&S.seq_ready[s]) != k) { }                   // the helper has digested this shape's previous pod
-      PROF_T(1)
-      const int4 q0 = ld_vol4(&S.pkg[s][0]), q1 = ld_vol4(&S.pkg[s][4]), q2 = ld_vol4(&S.pkg[s][8]), q3 = ld_vol4(&S.pkg[s][12]);
-      int flags = 0, bk = q3.y, tw = -1; uint32_t masks = 0; unsigned long long win = 0;
-      const int u = q1.w;
-      if (q2.z) {                                                 // general pod: the whole warp, any shape / state
-        reason = general_pod(S, a, lk, hpay, lane, p, s, ns);
-        if (reason) break;
-        flags = 4;
-        PROF_C(9, 1)
-      } else {
-        const int uu = max(u, 0);
-        const int vnow = S.ver[uu];
-        const unsigned long long xb = S.xbest[s];
-        const int xt = S.xbest_t[s];
-        const int rq_c = S.rq_core[s], rq_m = S.rq_mem[s];
-        unsigned long long tradekey = ((unsigned long long)(unsigned)q1.y << 32) | (unsigned)q1.x;
-        if (u >= 0 && vnow != q2.x) {                             // the node's rows changed since the helper's Trade
-          const int4 c0 = *reinterpret_cast<const int4 *>(&S.rc[uu][0]), c1 = *reinterpret_cast<const int4 *>(&S.rc[uu][4]);
-          const int4 m0 = *reinterpret_cast<const int4 *>(&S.rm[uu][0]), m1 = *reinterpret_cast<const int4 *>(&S.rm[uu][4]);
-          const int c[EGS_G] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-          const int m[EGS_G] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-          bk = trade_lanes(c, m, gl, rq_c, rq_m, a.policy);
-          const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
-          tradekey = bk >= 0 ? cand_key(sc, (uint32_t)q3.x) : 0ull;
-          PROF_C(14, 1)
-        }
-        unsigned long long best = ((unsigned long long)(unsigned)q0.y << 32) | (unsigned)q0.x;
-        const unsigned long long head = ((unsigned long long)(unsigned)q0.w << 32) | (unsigned)q0.z;
-        tw = q1.z; masks = (uint32_t)q2.y;
-        if (xb > best) { best = xb; tw = xt; masks = 0; }
-        if (tradekey > best) { best = tradekey; tw = u; masks = 1u << (bk & 7); }
-        const bool from_head = head > best;
-        win = from_head ? head : best;
-        int nT = 0;
-        if (q2.w) reason = 3;                                     // a truncated list ran dry
-        else if (from_head) { nT = S.nT; if (nT >= NT) reason = 2; }
-        if (reason) break;
-        if (win != 0) {
-          if (from_head) {
-            tw = nT;
-            const uint32_t w = key_node(win);
-            install_slot(S, a, head_payload(S, a, hpay, s, w), tw, w, ns, s, lane);
-            __syncwarp();
-            masks = S.al[s][tw] & 0xFFu;
-            flags |= 1;
-            PROF_C(11, 1)
-          } else if (masks == 0) {
-            masks = S.al[s][tw] & 0xFFu;                          // a slot another shape installed
-          }
-          const int g = __ffs(masks) - 1;
-          const int cc = S.rc[tw][g], mm = S.rm[tw][g];
-          const int ok = (cc >= rq_c && mm >= rq_m) ? 1 : 0;      // GPUs.Transact gpu.go:164-171
-          __syncwarp();
-          if (lane == 0) {
-            if (ok) { const int v = S.ver[tw]; st_vol(&S.ver[tw], v + 1); S.rc[tw][g] = cc - rq_c; S.rm[tw][g] = mm - rq_m; st_vol(&S.ver[tw], v + 2); }
-            S.dirty[tw] = 1;
-            if (from_head) { __threadfence_block(); st_vol(&S.nT, nT + 1); }
-          }
-          flags |= ok ? 2 : 0;
-          if (!ok) masks = 0;
-        }
-        if (lane == 0 && xb != 0) { S.xbest[s] = 0; S.xbest_t[s] = -1; }
-        PROF_C(6, 1)
-      }
-      // ---- tell the helper (mailbox, then the sequence number, then wake it)
-      if (lane == 0) {
-        *reinterpret_cast<int4 *>(&S.evt[s][0]) = make_int4((int)(unsigned)win, (int)(unsigned)(win >> 32), p, u);
-        *reinterpret_cast<int4 *>(&S.evt[s][4]) = make_int4(bk, tw, flags, (int)masks);
-        __threadfence_block();
-        st_vol(&S.seq_done[s], k + 1);
-        mbar_arrive(&S.mbar[s % nh]);
-      }
-      __syncwarp();
-#ifdef EGS_RESOLVE_PROF
-      { const long long n_ = clock64(); prof[(flags & 4) ? 4 : (flags & 1) ? 5 : 2] += n_ - tprev; tprev = n_; }
-#endif
-    }
-    // ---- the round ends before pod p (reason != 0) or all pods are done: wake every helper
-    if (lane == 0) { S.stop_reason = reason; S.stop_p = p; __threadfence_block(); st_vol(&S.stop, reason ? 1 : 2); }
-    __syncwarp();
-    if (lane < nh) mbar_arrive(&S.mbar[lane]);
-  } else if (warp < nh) {
-    // =========================================================== a helper: shapes s with s % nh == warp
-    unsigned ph = 0;
-    while (true) {
-      bool progressed = false;
-      const int stopping = ld_vol(&S.stop);
-      for (int s = warp; s < ns; s += nh) {
-        const int k = S.seq_ready[s];
-        if (ld_vol(&S.seq_done[s]) == k) continue;
-        __threadfence_block();
-        progressed = true;
-        // ---- digest pod k of shape s
-        const int4 e0 = ld_vol4(&S.evt[s][0]), e1 = ld_vol4(&S.evt[s][4]);
-        const int flags = e1.z;
-        if (!(flags & 4)) {
-          const unsigned long long win = ((unsigned long long)(unsigned)e0.y << 32) | (unsigned)e0.x;
-          const int p = e0.z, u = e0.w, bk = e1.x, tw = e1.y;
-          const int uu = max(u, 0);
-          const int sc = (bk >= 0 && a.policy == EGS_BINPACK) ? (bk >> 3) * 100 : 0;
-          const int fit = S.afit[s] + (bk >= 0);
-          const unsigned long long fd = S.afd[s] + (bk >= 0 ? S.fterm[uu] : 0ull);
-          const unsigned long long sd = S.asd[s] + (bk >= 0 ? score_term_b(S.sbase[uu], sc) : 0ull);
-          if (lane == 0) {
-            if (u >= 0 && u != tw) {                              // the pod's filter Traded slot u
-              if (bk >= 0) { S.st[s][u] = OPT_CACHED; S.al[s][u] = 1u << (bk & 7); S.tkey[s][u] = cand_key(sc, (uint32_t)S.node[u]); }
-              else S.st[s][u] = OPT_UNFIT;
-              S.pmask[s][u >> 5] &= ~(1u << (u & 31));
-            }
-            int o_node = -1, o_status = EGS_ERR_NOFIT;
-            if (win != 0) {                                       // node.go:90-92: the entry is consumed
-              S.st[s][tw] = OPT_ABSENT; S.tkey[s][tw] = 0; S.pmask[s][tw >> 5] |= 1u << (tw & 31);
-              S.afit[s] = fit - 1; S.afd[s] = fd - S.fterm[tw]; S.asd[s] = sd - score_term_b(S.sbase[tw], key_score(win));
-              S.pu[s] = tw;
-              o_node = S.node[tw]; o_status = (flags & 2) ? EGS_OK : EGS_ERR_TRANSACT;
-            } else {
-              S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd;
-              S.pu[s] = -1;
-            }
-            if (a.out.node) a.out.node[p] = o_node;
-            if (a.out.status) a.out.status[p] = o_status;
-            if (a.out.fit_count) a.out.fit_count[p] = fit;
-            if (a.out.fit_digest) a.out.fit_digest[p] = fd;
-            if (a.out.score_digest) a.out.score_digest[p] = sd;
-            if (a.out.alloc) reinterpret_cast<uint32_t *>(a.out.alloc)[p] = (uint32_t)e1.w;
-          }
-          __syncwarp();
-        }
-        // ---- prepare pod k+1 of shape s
-        int payload_d = -1, payload_c = 0; unsigned long long head = 0;
-        if (!stopping) {
-          maintain_heads(S, lk, D, rke, s, lane, false);
-          head = S.bh[s];
-          const int pu = S.pu[s];
-          const bool fast = mono && S.rq_single[s] && pu != -2 && ld_vol(&S.n_observed) == ns;
-          unsigned long long pre_best = 0, tradekey = 0; int pre_t = -1, v_pre = -1, bk_pre = -1; uint32_t pre_al = 0, und = 0;
-          if (fast) {
-            const int pre_nT = ld_vol(&S.nT);
-            __threadfence_block();
-            unsigned long long b = 0; int bt = -1;
-#pragma unroll 4
-            for (int t = lane; t < pre_nT; t += 32) { const unsigned long long kk = S.tkey[s][t]; if (kk > b) { b = kk; bt = t; } }
-            int owner;
-            pre_best = warp_max_key_fwd(b, owner);
-            pre_t = __shfl_sync(0xffffffffu, bt, owner);
-            pre_al = pre_t >= 0 ? (S.al[s][pre_t] & 0xFFu) : 0u;
-            if (pu >= 0) {                                        // Trade of the pending option on the rows as they are NOW
-              und = (uint32_t)S.node[pu];
-              v_pre = ld_vol(&S.ver[pu]);
-              int c[EGS_G], m[EGS_G];
-#pragma unroll
-              for (int g = 0; g < EGS_G; g++) { c[g] = ld_vol(&S.rc[pu][g]); m[g] = ld_vol(&S.rm[pu][g]); }
-              bk_pre = trade_lanes(c, m, gl, S.rq_core[s], S.rq_mem[s], a.policy);
-              if ((v_pre & 1) || ld_vol(&S.ver[pu]) != v_pre) v_pre = -1;   // a bind was writing the rows meanwhile
-              const int sc = (bk_pre >= 0 && a.policy == EGS_BINPACK) ? (bk_pre >> 3) * 100 : 0;
-              tradekey = bk_pre >= 0 ? cand_key(sc, und) : 0ull;
-            }
-          }
-          if (lane == 0) {
-            *reinterpret_cast<int4 *>(&S.pkg[s][0]) = make_int4((int)(unsigned)pre_best, (int)(unsigned)(pre_best >> 32), (int)(unsigned)head, (int)(unsigned)(head >> 32));
-            *reinterpret_cast<int4 *>(&S.pkg[s][4]) = make_int4((int)(unsigned)tradekey, (int)(unsigned)(tradekey >> 32), pre_t, pu);
-            *reinterpret_cast<int4 *>(&S.pkg[s][8]) = make_int4(v_pre, (int)pre_al, fast ? 0 : 1, S.dry[s]);
-            *reinterpret_cast<int4 *>(&S.pkg[s][12]) = make_int4((int)und, bk_pre, 0, 0);
-          }
-          if (hpay && head != 0 && S.hpay_node[s] != (int)key_node(head)) { payload_d = S.bh_d[s]; payload_c = S.cur[s][payload_d]; }
-        }
-        __syncwarp();
-        if (lane == 0) { __threadfence_block(); st_vol(&S.seq_ready[s], k + 1); }
-        __syncwarp();
-        // ---- after the hand-back: payload of the best head -> shared memory (a head-win finds it there)
-        if (payload_d >= 0) {
-          if (lane == 0) st_vol(&S.hpay_node[s], -1);
-          __syncwarp();
-          const int4 *src = reinterpret_cast<const int4 *>(a.bufs + (size_t)payload_d * a.L.bytes + a.L.off_cand + ((size_t)s * a.L.rkm + payload_c) * a.L.cand_bytes);
-          int4 *dst = reinterpret_cast<int4 *>(hpay + (size_t)s * a.L.cand_bytes);
-          for (int i = lane; i < a.L.cand_bytes / 16; i += 32) dst[i] = src[i];
-          __syncwarp();
-          if (lane == 0) { __threadfence_block(); st_vol(&S.hpay_node[s], (int)key_node(head)); }
-          __syncwarp();
-        }
-        PROF_T(0)
-      }
-      if (!progressed) {
-        if (stopping) break;
-        while (!mbar_try_wait(&S.mbar[warp], ph)) { if (ld_vol(&S.stop)) break; }
-        ph ^= 1u;
-      }
-    }
-  }
-  __syncthreads();
-  resolve_epilogue(S, a);
-#ifdef EGS_RESOLVE_PROF
-  if (lane == 0 && warp <= nh) for (int i = 0; i < 16; i++) atomicAdd((unsigned long long *)&a.ctl->prof[i], (unsigned long long)prof[i]);
 #endif
 }
 

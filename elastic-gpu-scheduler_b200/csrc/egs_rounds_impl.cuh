@@ -116,9 +116,6 @@ static int rounds_ensure(egs_handle *h, int P, const BufLayout &L) {
     CK(h, cudaFuncSetAttribute(k_resolve_mw<16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
     CK(h, cudaFuncSetAttribute(k_resolve_mw<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
     CK(h, cudaFuncSetAttribute(k_resolve_mw<RSMAX, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
-    CK(h, cudaFuncSetAttribute(k_resolve_tw<16, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
-    CK(h, cudaFuncSetAttribute(k_resolve_tw<32, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
-    CK(h, cudaFuncSetAttribute(k_resolve_tw<RSMAX, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MW_SMEM_MAX));
   }
   const size_t need = (size_t)L.bytes * RD;
   if (need > R.bufs_cap) {
@@ -228,8 +225,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   int rke = cfg.rkm;
   auto env_int = [](const char *k, int dflt) { const char *v = getenv(k); return v ? atoi(v) : dflt; };
   const int use_hpay = cfg.inst != 2 ? env_int("EGS_MW_HPAY", 2) : 0;   // prefetched candidate payload per shape (2: cp.async)
-  const int use_lmax = cfg.inst != 2 ? env_int("EGS_MW_LMAX", 0) : 0;   // cached column maxima of the tracked keys
-  const size_t hp_bytes = (use_hpay ? (size_t)ns_cfg * L.cand_bytes : 0) + (use_lmax ? (size_t)ns_cfg * 32 * 12 : 0);
+  const size_t hp_bytes = use_hpay ? (size_t)ns_cfg * L.cand_bytes : 0;
   {
     const size_t avail = MW_SMEM_MAX - cfg.smem_struct - hp_bytes;
     const size_t per = (size_t)ns_cfg * D * 8;
@@ -237,7 +233,6 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
     if (rke < 4) return fail(h, EGS_ERR_BAD_ARG, "rounds: shape set too large for the resolver's shared memory");
   }
   const int nw = std::max(1, std::min(ns_cfg, env_int("EGS_MW_WARPS", MW_MAX_WARPS)));
-  const int engine_tw = env_int("EGS_RESOLVER_TW", 0);
   const size_t smem = cfg.smem_struct + (size_t)ns_cfg * D * rke * 8 + hp_bytes;
 
   SelectArgs sa; MergeArgs ma; MwArgs ra;
@@ -249,7 +244,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   ma.out = R.d_bufs + (size_t)h->rank * L.bytes; ma.L = L; ma.ctl = R.d_ctl;
   ra.core = h->d_core; ra.mem = h->d_mem; ra.lo = h->lo; ra.hi = h->hi; ra.policy = h->policy; ra.n_shards = D;
   ra.rd = R.d_rd; ra.tb = tb; ra.obs_pending = R.d_obs; ra.bufs = R.d_bufs; ra.L = L; ra.pod_sidx = R.d_pod_sidx;
-  ra.p0 = -1; ra.p_limit = 0; ra.out = out; ra.ctl = R.d_ctl; ra.rke = rke; ra.nw = nw; ra.use_hpay = use_hpay; ra.use_lmax = use_lmax;
+  ra.p0 = -1; ra.p_limit = 0; ra.out = out; ra.ctl = R.d_ctl; ra.rke = rke; ra.nw = nw; ra.use_hpay = use_hpay;
 
   int ns_round = ns_cfg;                                        // grid of k_merge
   bool local_copied = false;
@@ -278,15 +273,9 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
     } else if (h->world > 1)
       NCK(h, nccl_api()->AllGather(R.d_bufs + (size_t)h->rank * L.bytes, R.d_bufs, (size_t)L.bytes, ncclChar, (ncclComm_t)R.comm, h->stream));
     if (h->timing) CK(h, cudaEventRecord(ev[2], h->stream));
-    if (engine_tw) {                                            // one ticket warp + nw helper warps
-      if (cfg.inst == 0) k_resolve_tw<16, 512><<<1, 32 * (nw + 1), smem, h->stream>>>(ra);
-      else if (cfg.inst == 1) k_resolve_tw<32, 256><<<1, 32 * (nw + 1), smem, h->stream>>>(ra);
-      else k_resolve_tw<RSMAX, 128><<<1, 32 * (nw + 1), smem, h->stream>>>(ra);
-    } else {                                                    // one owner warp per shape, ticket passed between them
-      if (cfg.inst == 0) k_resolve_mw<16, 512><<<1, 32 * nw, smem, h->stream>>>(ra);
-      else if (cfg.inst == 1) k_resolve_mw<32, 256><<<1, 32 * nw, smem, h->stream>>>(ra);
-      else k_resolve_mw<RSMAX, 128><<<1, 32 * nw, smem, h->stream>>>(ra);
-    }
+    if (cfg.inst == 0) k_resolve_mw<16, 512><<<1, 32 * nw, smem, h->stream>>>(ra);
+    else if (cfg.inst == 1) k_resolve_mw<32, 256><<<1, 32 * nw, smem, h->stream>>>(ra);
+    else k_resolve_mw<RSMAX, 128><<<1, 32 * nw, smem, h->stream>>>(ra);
     if (h->timing) CK(h, cudaEventRecord(ev[3], h->stream));
     h->k_launches[EGS_K_SELECT] += 1; h->k_launches[EGS_K_MERGE] += 1; h->k_launches[EGS_K_RESOLVE] += 1;
     return EGS_OK;
