@@ -62,7 +62,8 @@ static int read_units_alloc(char **tok, egs_unit *u, int32_t *off, int32_t *idx)
 int main(int argc, char **argv) {
   int policy = argc > 1 ? atoi(argv[1]) : 0;
   if (egs_create(policy, MAXN, EGS_MAX_GPUS, 0, &H) != EGS_OK) { fprintf(stderr, "egs_create failed\n"); return 2; }
-  char line[1 << 16];
+  static char line[1 << 16];
+  setvbuf(stdout, NULL, _IOLBF, 1 << 16);            /* every answer line reaches the driver at once */
   while (fgets(line, sizeof line, stdin)) {
     char *tok = NULL;
     char *cmd = strtok_r(line, " \n", &tok);
