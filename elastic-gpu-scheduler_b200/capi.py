@@ -98,8 +98,9 @@ def load(build: bool = True):
     return L
 
 
+EGS_MAX_CONTAINERS_APPLY = 8
 MUTATION_DTYPE = np.dtype([("kind", "<i4"), ("node_id", "<i4"), ("n_containers", "<i4"), ("pad", "<i4"),
-                           ("units", "<i4", (4, 3)), ("n_idx", "i1", (4,)), ("idx", "i1", (4, 8)), ("uid", "<u8")], align=True)
+                           ("units", "<i4", (8, 3)), ("n_idx", "i1", (8,)), ("idx", "i1", (8, 8)), ("uid", "<u8")], align=True)
 EGS_MUT_ADD, EGS_MUT_FORGET, EGS_MUT_REPLAY = 0, 1, 2
 
 

@@ -125,8 +125,8 @@ static int grow_slots(egs_handle *h, int need) {
   return EGS_OK;
 }
 
-static int check_units(int C, const egs_unit *u) {
-  if (C < 1 || C > EGS_C || !u) return EGS_ERR_BAD_ARG;
+static int check_units(int C, const egs_unit *u, int max_c = EGS_C) {
+  if (C < 1 || C > max_c || !u) return EGS_ERR_BAD_ARG;
   for (int i = 0; i < C; i++) {
     if (u[i].count < 0) return EGS_ERR_BAD_ARG;
     if (u[i].core < -1 || u[i].mem < -1) return EGS_ERR_BAD_ARG;
@@ -187,6 +187,12 @@ static int intern_slow(egs_handle *h, int C, const egs_unit *u, int *slot) {
   return EGS_OK;
 }
 
+static ReqW make_req_w(int C, const egs_unit *u) {
+  ReqW r; memset(&r, 0, sizeof r);
+  r.C = C;
+  for (int i = 0; i < C; i++) { r.core[i] = u[i].core; r.mem[i] = u[i].mem; r.cnt[i] = u[i].count; }
+  return r;
+}
 static Req make_req(int C, const egs_unit *u) {
   Req r; memset(&r, 0, sizeof r);
   r.C = C;
@@ -641,7 +647,7 @@ static int apply_lists(egs_handle *h, int cancel, int node_id, int C, const egs_
                        const int32_t *alloc_off, const int32_t *alloc_idx) {
   ApplyArgs a; memset(&a, 0, sizeof a);
   a.core = h->d_core; a.mem = h->d_mem; a.mem_total = h->d_mem_total; a.node = node_id;
-  a.req = make_req(C, units); a.cancel = cancel;
+  a.req = make_req_w(C, units); a.cancel = cancel;
   a.all_st = h->d_st; a.slot_stride = (size_t)h->n_pad; a.n_slots = (int)h->shapes.size();
   for (int c = 0; c < C; c++) {
     int n = alloc_off ? alloc_off[c + 1] - alloc_off[c] : 0;
@@ -665,7 +671,7 @@ extern "C" int egs_pod_apply(egs_handle *h, int node_id, int n_containers, const
   Guard g(h);
   if (node_id < 0 || node_id >= h->max_nodes) return EGS_ERR_BAD_ARG;
   if (h->h_gpu_count[node_id] == 0) return EGS_ERR_NO_NODE;
-  TRY(check_units(n_containers, units));
+  TRY(check_units(n_containers, units, EGS_MAX_CONTAINERS_APPLY));
   TRY(flush_pending(h));
   if (in_pod_maps(h, uid)) return EGS_OK;                                   // scheduler.go:239-241
   if (!in_pods_map(h, node_id, uid)) {                                      // node.go:149
@@ -683,7 +689,7 @@ extern "C" int egs_node_replay_pod(egs_handle *h, int node_id, int n_containers,
   Guard g(h);
   if (node_id < 0 || node_id >= h->max_nodes) return EGS_ERR_BAD_ARG;
   if (h->h_gpu_count[node_id] == 0) return EGS_ERR_NO_NODE;
-  TRY(check_units(n_containers, units));
+  TRY(check_units(n_containers, units, EGS_MAX_CONTAINERS_APPLY));
   TRY(flush_pending(h));
   if (!in_pods_map(h, node_id, uid)) {
     TRY(apply_lists(h, 0, node_id, n_containers, units, alloc_off, alloc_idx));
@@ -701,7 +707,7 @@ extern "C" int egs_pod_cancel(egs_handle *h, int node_id, int n_containers, cons
   if (node_id >= 0) {
     if (node_id >= h->max_nodes) return EGS_ERR_BAD_ARG;
     if (h->h_gpu_count[node_id] == 0) return EGS_ERR_NO_NODE;
-    TRY(check_units(n_containers, units));
+    TRY(check_units(n_containers, units, EGS_MAX_CONTAINERS_APPLY));
     if (in_pods_map(h, node_id, uid)) {                                     // node.go:131
       TRY(apply_lists(h, 1, node_id, n_containers, units, alloc_off, alloc_idx));
       if (!h->pods_map.erase(NodeUid{node_id, uid})) h->auto_gone_node.insert(NodeUid{node_id, uid});
@@ -726,7 +732,7 @@ static int mutations_apply_locked(egs_handle *h, int n, const egs_mutation *ops)
     if (m.node_id < 0) { if (m.kind != EGS_MUT_FORGET) return EGS_ERR_BAD_ARG; continue; }
     if (m.node_id >= h->max_nodes) return EGS_ERR_BAD_ARG;
     if (h->h_gpu_count[m.node_id] == 0) return EGS_ERR_NO_NODE;
-    TRY(check_units(m.n_containers, m.units));
+    TRY(check_units(m.n_containers, m.units, EGS_MAX_CONTAINERS_APPLY));
     for (int c = 0; c < m.n_containers; c++) {
       if (m.n_idx[c] < 0 || m.n_idx[c] > EGS_G) return EGS_ERR_BAD_ARG;
       for (int j = 0; j < m.n_idx[c]; j++) if (m.idx[c][j] < 0 || m.idx[c][j] >= h->h_gpu_count[m.node_id]) return EGS_ERR_BAD_ARG;
@@ -736,7 +742,7 @@ static int mutations_apply_locked(egs_handle *h, int n, const egs_mutation *ops)
   std::vector<ApplyOp> dev; dev.reserve((size_t)n);
   auto push = [&](const egs_mutation &m, int cancel) {
     ApplyOp o; memset(&o, 0, sizeof o);
-    o.node = m.node_id; o.cancel = cancel; o.req = make_req(m.n_containers, m.units);
+    o.node = m.node_id; o.cancel = cancel; o.req = make_req_w(m.n_containers, m.units);
     for (int c = 0; c < m.n_containers; c++) { o.n_idx[c] = m.n_idx[c]; for (int j = 0; j < m.n_idx[c]; j++) o.idx[c][j] = m.idx[c][j]; }
     dev.push_back(o);
   };

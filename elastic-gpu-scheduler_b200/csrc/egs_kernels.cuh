@@ -289,10 +289,12 @@ __global__ void k_bind(BindArgs a) {
 
 // AddPod / ForgetPod with the option rebuilt from annotations (allocate.go:75-93):
 // explicit index lists, Transact (gpu.go:153-175) or Cancel (gpu.go:177-191).
+#define EGS_CA EGS_MAX_CONTAINERS_APPLY
+struct ReqW { int C; int core[EGS_CA], mem[EGS_CA], cnt[EGS_CA]; };   // a pod as AddPod / ForgetPod see it (up to 8 containers)
 struct ApplyArgs {
   int32_t *core, *mem; const int32_t *mem_total;
-  int node; Req req;
-  int n_idx[EGS_C]; int8_t idx[EGS_C][EGS_G];
+  int node; ReqW req;
+  int n_idx[EGS_CA]; int8_t idx[EGS_CA][EGS_G];
   uint8_t *all_st; size_t slot_stride; int n_slots;
   int cancel;
 };
@@ -323,7 +325,7 @@ __global__ void k_apply(ApplyArgs a) {
 
 // Many AddPod / ForgetPod row updates in ONE launch: the host has grouped the records by node (record order kept
 // inside a node); one thread per touched node applies its run with the arithmetic of k_apply.
-struct ApplyOp { int node, cancel; Req req; int n_idx[EGS_C]; int8_t idx[EGS_C][EGS_G]; };
+struct ApplyOp { int node, cancel; ReqW req; int n_idx[EGS_CA]; int8_t idx[EGS_CA][EGS_G]; };
 struct ApplyManyArgs {
   int32_t *core, *mem; const int32_t *mem_total;
   const ApplyOp *ops; const int32_t *group_off; int n_groups;   // group g = ops[group_off[g] .. group_off[g+1])

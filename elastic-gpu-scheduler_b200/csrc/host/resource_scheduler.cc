@@ -28,14 +28,16 @@ bool CudaUnitScheduler::Handles(const Pod &pod) {
   return false;
 }
 
-bool CudaUnitScheduler::RequestOf(const Pod &pod, std::vector<egs_unit> *out) {
+// max_containers: EGS_MAX_CONTAINERS for the verbs that Trade (Assume / Score / Bind), EGS_MAX_CONTAINERS_APPLY for the
+// ones that only account a pod somebody placed (AddPod / ForgetPod / replay)
+bool CudaUnitScheduler::RequestOf(const Pod &pod, std::vector<egs_unit> *out, size_t max_containers) {
   out->clear();
   for (const auto &c : pod.containers) {
     egs_unit u;
     if (egs_unit_from_requests(requestOf(c, kResourceGPUCore), requestOf(c, kResourceGPUMemory), &u) != EGS_OK) return false;
     out->push_back(u);
   }
-  return !out->empty() && out->size() <= EGS_MAX_CONTAINERS;
+  return !out->empty() && out->size() <= max_containers;
 }
 
 std::string CudaUnitScheduler::RequestString(const std::vector<egs_unit> &req) {
@@ -87,9 +89,9 @@ int CudaUnitScheduler::getNodeInfo(const std::string &name, std::string *err) {
   node_ids_.emplace(name, id);
   for (const auto &p : info.assumed_pods) {                                                    // node.go:52-54: na.Add(&pods[i], nil)
     std::vector<egs_unit> req;
-    if (!RequestOf(p, &req)) {                   // not representable on the device path: say so, loudly -- the node's rows
+    if (!RequestOf(p, &req, EGS_MAX_CONTAINERS_APPLY)) {   // not representable on the device path: say so, loudly -- the node's rows
       fprintf(stderr, "libegs: assumed pod %s/%s on node %s has more than %d containers (or an out-of-range request): "   // would
-              "its GPU share is NOT subtracted from the node cache\n", p.ns.c_str(), p.name.c_str(), name.c_str(), EGS_MAX_CONTAINERS);  // otherwise be silently wrong
+              "its GPU share is NOT subtracted from the node cache\n", p.ns.c_str(), p.name.c_str(), name.c_str(), EGS_MAX_CONTAINERS_APPLY);  // otherwise be silently wrong
       unsupported_.push_back(p.ns + "/" + p.name);
       continue;
     }
@@ -188,9 +190,9 @@ std::string CudaUnitScheduler::AddPod(const Pod &pod) {
   int id = getNodeInfo(pod.node_name, &err);
   if (id < 0) return err;
   std::vector<egs_unit> req;
-  if (!RequestOf(pod, &req)) {                 // never drop silently: the caller (controller.go:330) logs the error
+  if (!RequestOf(pod, &req, EGS_MAX_CONTAINERS_APPLY)) {   // never drop silently: the caller (controller.go:330) logs the error
     unsupported_.push_back(pod.ns + "/" + pod.name);
-    return "libegs: pod " + pod.ns + "/" + pod.name + " has more than 4 containers (or an out-of-range request): not accounted on the device path";
+    return "libegs: pod " + pod.ns + "/" + pod.name + " has more than 8 containers (or an out-of-range request): not accounted on the device path";
   }
   std::vector<int32_t> off, idx;
   optionFromPod(pod, &off, &idx);
@@ -207,7 +209,7 @@ std::string CudaUnitScheduler::ForgetPod(const Pod &pod) {
   }
   std::vector<egs_unit> req;
   std::vector<int32_t> off, idx;
-  if (!RequestOf(pod, &req)) { req.assign(1, egs_unit{-1, -1, 0}); off = {0, 0}; idx = {0}; }
+  if (!RequestOf(pod, &req, EGS_MAX_CONTAINERS_APPLY)) { req.assign(1, egs_unit{-1, -1, 0}); off = {0, 0}; idx = {0}; }
   else optionFromPod(pod, &off, &idx);
   egs_pod_cancel(h_, id, (int)req.size(), req.data(), off.data(), idx.data(), uidOf(pod.uid));
   return "";

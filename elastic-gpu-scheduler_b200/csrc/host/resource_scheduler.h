@@ -74,7 +74,7 @@ class CudaUnitScheduler : public ResourceScheduler {
   // GetResourceScheduler (scheduler.go:323-334): does any container request a managed resource?
   static bool Handles(const Pod &pod);
   // NewGPURequest (allocate.go:35-58)
-  static bool RequestOf(const Pod &pod, std::vector<egs_unit> *out);
+  static bool RequestOf(const Pod &pod, std::vector<egs_unit> *out, size_t max_containers = EGS_MAX_CONTAINERS);
   // GPURequest.String (allocate.go:22-28)
   static std::string RequestString(const std::vector<egs_unit> &req);
 

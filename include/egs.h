@@ -37,7 +37,8 @@ extern "C" {
 #endif
 
 #define EGS_MAX_GPUS        8      /* GPUs per node the SoA row holds                      */
-#define EGS_MAX_CONTAINERS  4      /* containers per pod the device path enumerates        */
+#define EGS_MAX_CONTAINERS  4      /* containers per pod the filter / score / bind path enumerates */
+#define EGS_MAX_CONTAINERS_APPLY 8 /* containers per pod AddPod / ForgetPod / replay account (sidecars count) */
 #define EGS_CORE_PER_GPU    100    /* utils.GPUCoreEachCard, pkg/utils/types.go:6          */
 #define EGS_MAX_MEM_PER_GPU (1 << 25) /* int32 guard: Range/(k+1)*100 must fit int32 (Go int is 64-bit) */
 #define EGS_MAX_CORE_LOAD   (1 << 20) /* bound for free_core values given to egs_state_load */
@@ -125,7 +126,10 @@ int egs_option_dump(egs_handle *h, int n_containers, const egs_unit *units, int 
 
 /* AddPod (scheduler.go:229-245 -> node.go:148-160 with the option rebuilt from the
  * annotations, allocate.go:75-93).  alloc_idx[alloc_off[c] .. alloc_off[c+1]) are the
- * GPU indices of container c in annotation order. */
+ * GPU indices of container c in annotation order.  The three accounting verbs below (and the mutation records)
+ * take pods of up to EGS_MAX_CONTAINERS_APPLY containers: a pod another scheduler placed -- sidecars included --
+ * is subtracted from the node cache exactly like the reference does, also when this library could not have
+ * scheduled it (filter / score / bind stop at EGS_MAX_CONTAINERS). */
 int egs_pod_apply(egs_handle *h, int node_id, int n_containers, const egs_unit *units,
                   const int32_t *alloc_off, const int32_t *alloc_idx, uint64_t uid);
 /* NodeAllocator.Add(pod, nil) alone (node.go:148-160), as NewNodeAllocator replays the pods already
@@ -143,9 +147,9 @@ enum egs_mutation_kind { EGS_MUT_ADD = 0,      /* AddPod     == egs_pod_apply   
                          EGS_MUT_REPLAY = 2 }; /* NodeAllocator.Add at node load == egs_node_replay_pod */
 typedef struct egs_mutation {
   int32_t kind, node_id, n_containers, pad;
-  egs_unit units[EGS_MAX_CONTAINERS];
-  int8_t n_idx[EGS_MAX_CONTAINERS];                     /* GPU indices of container c in annotation order ...      */
-  int8_t idx[EGS_MAX_CONTAINERS][EGS_MAX_GPUS];         /* ... idx[c][0 .. n_idx[c])                                */
+  egs_unit units[EGS_MAX_CONTAINERS_APPLY];
+  int8_t n_idx[EGS_MAX_CONTAINERS_APPLY];               /* GPU indices of container c in annotation order ...      */
+  int8_t idx[EGS_MAX_CONTAINERS_APPLY][EGS_MAX_GPUS];   /* ... idx[c][0 .. n_idx[c])                                */
   uint64_t uid;
 } egs_mutation;
 /* Applies the records IN ORDER -- observably identical to issuing the single-pod verbs one by one -- with ONE kernel

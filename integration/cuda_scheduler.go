@@ -98,9 +98,11 @@ func uidKey(uid types.UID) C.uint64_t {
 }
 
 // requestOf == NewGPURequest (allocate.go:35-58) through egs_unit_from_requests.
-func (d *CudaUnitScheduler) requestOf(pod *v1.Pod) ([]C.egs_unit, error) {
-	if len(pod.Spec.Containers) > C.EGS_MAX_CONTAINERS {
-		return nil, fmt.Errorf("pod %s/%s: more than %d containers are handled by the CPU scheduler", pod.Namespace, pod.Name, int(C.EGS_MAX_CONTAINERS))
+// maxContainers: EGS_MAX_CONTAINERS for the verbs that Trade (Assume / Score / Bind), EGS_MAX_CONTAINERS_APPLY for the
+// ones that only account a pod somebody placed (AddPod / ForgetPod / replay at node load).
+func (d *CudaUnitScheduler) requestOf(pod *v1.Pod, maxContainers int) ([]C.egs_unit, error) {
+	if len(pod.Spec.Containers) > maxContainers {
+		return nil, fmt.Errorf("pod %s/%s: more than %d containers are not handled by the device path", pod.Namespace, pod.Name, maxContainers)
 	}
 	units := make([]C.egs_unit, len(pod.Spec.Containers))
 	for i := range pod.Spec.Containers {
@@ -166,7 +168,7 @@ func (d *CudaUnitScheduler) getNodeID(name string) (int32, error) {
 	d.nodeName = append(d.nodeName, name)
 	for i := range pods.Items {
 		pod := &pods.Items[i]
-		units, err := d.requestOf(pod)
+		units, err := d.requestOf(pod, C.EGS_MAX_CONTAINERS_APPLY)
 		if err != nil {
 			log.Errorf("replay of pod %s/%s on node %s skipped: %v", pod.Namespace, pod.Name, name, err)
 			continue
@@ -183,7 +185,7 @@ func (d *CudaUnitScheduler) Assume(nodes []string, pod *v1.Pod) ([]string, map[s
 	defer d.lock.Unlock()
 	filteredNodes := []string{}
 	failedNodes := map[string]string{}
-	units, err := d.requestOf(pod)
+	units, err := d.requestOf(pod, C.EGS_MAX_CONTAINERS)
 	if err != nil {
 		return nil, nil, err
 	}
@@ -227,7 +229,7 @@ func (d *CudaUnitScheduler) Score(nodes []string, pod *v1.Pod) []int {
 	d.lock.Lock()
 	defer d.lock.Unlock()
 	scores := make([]int, len(nodes))
-	units, err := d.requestOf(pod)
+	units, err := d.requestOf(pod, C.EGS_MAX_CONTAINERS)
 	if err != nil {
 		return scores
 	}
@@ -277,7 +279,7 @@ func (d *CudaUnitScheduler) Bind(node string, pod *v1.Pod) (err error) {
 	if err != nil {
 		return err
 	}
-	units, err := d.requestOf(pod)
+	units, err := d.requestOf(pod, C.EGS_MAX_CONTAINERS)
 	if err != nil {
 		return err
 	}
@@ -334,7 +336,7 @@ func (d *CudaUnitScheduler) AddPod(pod *v1.Pod) error {
 	if _, ok := d.podMaps[pod.UID]; ok {
 		return nil
 	}
-	units, err := d.requestOf(pod)
+	units, err := d.requestOf(pod, C.EGS_MAX_CONTAINERS_APPLY)
 	if err != nil {
 		return err
 	}
@@ -354,7 +356,7 @@ func (d *CudaUnitScheduler) ForgetPod(pod *v1.Pod) error {
 		if err != nil {
 			return err
 		}
-		units, err := d.requestOf(pod)
+		units, err := d.requestOf(pod, C.EGS_MAX_CONTAINERS_APPLY)
 		if err != nil {
 			return err
 		}

@@ -68,8 +68,8 @@ int main(int argc, char **argv) {
     char *tok = NULL;
     char *cmd = strtok_r(line, " \n", &tok);
     if (!cmd) continue;
-    egs_unit u[EGS_MAX_CONTAINERS];
-    int32_t off[EGS_MAX_CONTAINERS + 1], idx[64];
+    egs_unit u[EGS_MAX_CONTAINERS_APPLY];
+    int32_t off[EGS_MAX_CONTAINERS_APPLY + 1], idx[64];
     if (!strcmp(cmd, "NODE")) {
       char *name = strtok_r(NULL, " \n", &tok);
       long long core = atoll(strtok_r(NULL, " \n", &tok)), mem = atoll(strtok_r(NULL, " \n", &tok));

@@ -131,3 +131,39 @@ def test_node_reload_after_auto_uid_batch_drops_pods_map():
     assert e.pod_cancel(0, [(20, 4, 0)], [[g]], uid) == 0                       # not in the node's podsMap any more
     assert e.rows(0) == [(100, 16), (100, 16)]                                  # -> Cancel must not run
     assert e.pod_released(uid)                                                  # scheduler-level podMaps had it
+
+
+def test_accounting_verbs_take_pods_with_up_to_8_containers():
+    """A pod with sidecars (6 containers: 4 without GPU request = {-1,-1} sentinel units, gpu.go:9-13 / allocate.go:41-45)
+    that ANOTHER scheduler placed must be subtracted from the node cache exactly like the reference does (AddPod,
+    replay at node load, ForgetPod, the bulk mutation stream) even though this library's filter / score / bind stop at
+    4 containers -- otherwise a restarted scheduler would over-commit the node."""
+    import oracle_c as oc
+    eg = _eg(); cap = eg.capi
+    req = [(-1, -1, 0), (30, 4, 0), (-1, -1, 0), (0, 0, 2), (-1, -1, 0), (20, 2, 0)]
+    alloc = [[0], [1], [1], [2, 3], [3], [1]]
+    o = oc.OracleC(0)
+    o.add_node(400, 64)
+    e = eg.Egs(0, 2)
+    assert e.node_set_allocatable(0, 400, 64) == 0
+    # AddPod
+    assert e.pod_apply(0, req, alloc, 41) == 0
+    o.add_pod(0, req, alloc, 41)
+    assert e.rows(0) == o.rows(0) and e.pod_known(41)
+    # ForgetPod gives everything back (Cancel is unchecked, gpu.go:177-191)
+    assert e.pod_cancel(0, req, alloc, 41) == 0
+    o.forget_pod(0, req, alloc, 41)
+    assert e.rows(0) == o.rows(0) and e.pod_released(41)
+    # the same through the bulk mutation stream, incl. an 8-container pod
+    req8 = req + [(10, 1, 0), (-1, -1, 0)]
+    alloc8 = alloc + [[0], [0]]
+    assert e.mutations_apply([(cap.EGS_MUT_REPLAY, 0, req, alloc, 51), (cap.EGS_MUT_ADD, 0, req8, alloc8, 52),
+                              (cap.EGS_MUT_FORGET, 0, req, alloc, 51)]) == 0
+    o.add_pod(0, req, alloc, 51); o.add_pod(0, req8, alloc8, 52); o.forget_pod(0, req, alloc, 51)
+    assert e.rows(0) == o.rows(0)
+    # 9 containers: refused loudly, nothing applied; filter with 6 containers: refused (device path enumerates <= 4)
+    before = e.rows(0)
+    assert e.pod_apply(0, req8 + [(5, 1, 0)], alloc8 + [[0]], 60) == cap.EGS_ERR_BAD_ARG
+    assert e.rows(0) == before
+    with pytest.raises(cap.EgsError):
+        e.filter([0], req)
