@@ -405,10 +405,11 @@ struct MwSmem {
   unsigned long long tkey[NS][NT];   // cand_key of a tracked node's option when it is fit (CACHED/NEW), else 0
   unsigned long long hkey[NS][RD];   // current head of each untracked list (0 = none); may be STALE (see maintain_heads)
   unsigned long long afd[NS], asd[NS], bh[NS];             // aggregates; best head over the shards
+  unsigned long long dbound[NS];     // largest LAST key of an exhausted truncated list: unseen nodes stay below it (0: none)
   unsigned long long xbest[NS];      // best key among slots OTHER shapes installed since the owner's last ticket
   uint32_t al[NS][NT];               // option.Allocated masks
   unsigned pmask[NS][NT / 32];       // tracked slots whose option is ABSENT: Trade at the shape's next pod
-  int afit[NS], bh_d[NS], dry[NS], observed[NS], xbest_t[NS], hv_nT[NS], hpay_node[NS];
+  int afit[NS], bh_d[NS], observed[NS], xbest_t[NS], hv_nT[NS], hpay_node[NS];
   int pu[NS];                        // summary of pmask[s]: -1 none, t >= 0 exactly slot t, -2 unknown / several
   int rq_single[NS], rq_core[NS], rq_mem[NS]; uint32_t rq_cmask[NS];
   uint8_t st[NS][NT];                // OPT_*
@@ -468,31 +469,33 @@ __device__ __forceinline__ void hset_add(SM &S, uint32_t node) {   // one lane, 
 
 // The untracked candidate lists of shape s belong to its owner warp and are maintained LAZILY, outside the ticket:
 // entries whose node is tracked by now are skipped.  A head may therefore be STALE (its node became tracked after
-// this ran) -- harmless in the FAST regime (monotone round, every shape observed): only the owner itself changes
-// the tracked options of its shape, so that node's tracked option still carries the very same key, max(tracked) >=
-// stale head, and the stale head can never win; a head that does win is untracked, hence valid.  Outside the fast
-// regime (not-yet-observed NEW options are voided by other shapes' binds) general_pod re-validates the heads inside
-// the ticket (force).  Lanes d < D work on list (s, d).
+// this ran).  What the ticket may rely on, whatever the timing of this maintenance:
+//   * U = max(bh[s], dbound[s]) is an UPPER BOUND of the key of every untracked candidate of the shape: a list is
+//     sorted, so its (possibly stale) head bounds its later entries and -- when truncated -- the unseen nodes; an
+//     exhausted truncated list is bounded by its last key (dbound).  best tracked >= U  =>  a tracked option wins.
+//   * otherwise the ticket re-runs this maintenance INSIDE the ordered section (force), where the tracked set is
+//     exact, and decides on exact heads.  Every decision -- in particular where a round stops -- is thus a function
+//     of the serial state only, never of timing: the replicated resolvers of a sharded run stay in lock step.
+// Lanes d < D work on list (s, d).
 template <class SM>
 __device__ __forceinline__ void maintain_heads(SM &S, const unsigned long long *lk, int D, int rke, int s, int lane, bool force) {
   const int nT = ld_vol(&S.nT);
   if (!force && S.hv_nT[s] == nT) return;                       // no node became tracked since the last look
-  unsigned long long k = 0; int dryl = 0;
+  unsigned long long k = 0, db = 0;
   if (lane < D) {
     const int d = lane;
     int c = S.cur[s][d];
     const int len = S.len[s][d];
     const unsigned long long *l = lk + ((size_t)s * D + d) * rke;
     while (c < len) { k = l[c]; if (!hset_has(S, key_node(k))) break; c++; }
-    if (c >= len) k = 0;
+    if (c >= len) { k = 0; if (S.more[s][d] != 0 && len > 0) db = l[len - 1]; }
     S.cur[s][d] = (uint8_t)c;
     S.hkey[s][d] = k;
-    dryl = (k == 0 && S.more[s][d] != 0);
   }
-  int owner;
+  int owner, o2;
   const unsigned long long b = warp_max_key_fwd(k, owner);
-  const unsigned anydry = __ballot_sync(0xffffffffu, dryl);
-  if (lane == 0) { S.bh[s] = b; S.bh_d[s] = b ? owner : 0; S.dry[s] = anydry != 0; S.hv_nT[s] = nT; }
+  const unsigned long long dbm = warp_max_key_fwd(db, o2);
+  if (lane == 0) { S.bh[s] = b; S.bh_d[s] = b ? owner : 0; S.dbound[s] = dbm; S.hv_nT[s] = nT; }
   __syncwarp();
 }
 
@@ -583,7 +586,6 @@ __device__ __noinline__ int general_pod(SM &S, const MwArgs &a, const unsigned l
   int nT = S.nT;
   if (nT >= SM::HS / 2) return 2;                               // no free tracked slot for a new winner
   maintain_heads(S, lk, a.n_shards, a.rke, s, lane, true);      // inside the ticket the tracked set is exact
-  if (S.dry[s]) return 3;                                       // a truncated list ran dry: next round
   if (lane == 0) { S.xbest[s] = 0; S.xbest_t[s] = -1; }         // the scan below sees every slot
   if (!S.observed[s]) {                                         // first pod of this shape in the round:
     for (int t = lane; t < nT; t += 32) if (S.st[s][t] == OPT_NEW) S.st[s][t] = OPT_CACHED;   // NEW options are now ordinary
@@ -669,6 +671,10 @@ __device__ __noinline__ int general_pod(SM &S, const MwArgs &a, const unsigned l
   const unsigned long long head = S.bh[s];
   const bool from_head = head > tbest;
   const unsigned long long win = from_head ? head : tbest;
+  // a truncated list ran dry and what it did not show could beat the winner: the round must end (exact: the heads were
+  // re-validated inside this ticket).  NOTE: the pending options Traded above stay Traded -- that is what the next
+  // round's first filter of this shape would do on the same rows.
+  if (S.dbound[s] > win) return 3;
   const int fitc = S.afit[s];
   const unsigned long long ofd = S.afd[s], osd = S.asd[s];
   // ---- commit: NodeAllocator.Allocate (node.go:87-104) on the tracked copy, or NOFIT
@@ -783,7 +789,7 @@ __device__ __noinline__ bool resolve_prologue(SM &S, const MwArgs &a, unsigned l
       S.cur[s][d] = 0; S.len[s][d] = (uint8_t)len; S.more[s][d] = (uint8_t)more; S.hkey[s][d] = 0;
     }
     S.afit[s] = fit; S.afd[s] = fd; S.asd[s] = sd; S.observed[s] = 0; S.pu[s] = -1;
-    S.xbest[s] = 0; S.xbest_t[s] = -1; S.hv_nT[s] = -1; S.hpay_node[s] = -1; S.bh[s] = 0; S.bh_d[s] = 0; S.dry[s] = 0;
+    S.xbest[s] = 0; S.xbest_t[s] = -1; S.hv_nT[s] = -1; S.hpay_node[s] = -1; S.bh[s] = 0; S.bh_d[s] = 0; S.dbound[s] = 0;
     if (s < ns) {
       S.reqs[s] = a.rd->reqs[s];
       const Req &r = a.rd->reqs[s];
@@ -949,8 +955,8 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
       // fast pods: the best tracked option of s over the slots seen so far, and everything the ticket will need
       unsigned long long pre_best = 0; int pre_t = -1;
       const int u = pu, uu = max(pu, 0);
-      uint32_t und = 0, pre_al = 0; unsigned long long ft_u = 0, sb_u = 0, afd = 0, asd = 0;
-      int rq_c = 0, rq_m = 0, afit = 0, dry = 0, v_pre = -1, bk_pre = -1;
+      uint32_t und = 0, pre_al = 0; unsigned long long ft_u = 0, sb_u = 0, afd = 0, asd = 0, dbp = 0;
+      int rq_c = 0, rq_m = 0, afit = 0, v_pre = -1, bk_pre = -1;
       if (fast) {
         const int pre_nT = ld_vol(&S.nT);
         __threadfence_block();
@@ -963,7 +969,7 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
         pre_al = pre_t >= 0 ? (S.al[s][pre_t] & 0xFFu) : 0u;
         und = (uint32_t)S.node[uu]; ft_u = S.fterm[uu]; sb_u = S.sbase[uu];
         rq_c = S.rq_core[s]; rq_m = S.rq_mem[s];
-        afit = S.afit[s]; afd = S.afd[s]; asd = S.asd[s]; dry = S.dry[s];
+        afit = S.afit[s]; afd = S.afd[s]; asd = S.asd[s]; dbp = S.dbound[s];
         if (u >= 0) {                                             // Trade of the pending option on the rows as they are NOW;
           v_pre = ld_vol(&S.ver[uu]);                             // the ticket reuses it when no bind touched the node since
           int c[EGS_G], m[EGS_G];
@@ -1005,11 +1011,29 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
         unsigned long long best = pre_best; int tw = pre_t; uint32_t masks = pre_al;
         if (xb > best) { best = xb; tw = xt; masks = 0; }
         if (tradekey > best) { best = tradekey; tw = u; masks = 1u << (bk & 7); }
-        const bool from_head = head > best;
-        const unsigned long long win = from_head ? head : best;
+        // Exact rule (head*, dbound* = the exact values at this ticket): dbound* > max(head*, best) -> the round ends;
+        // head* > best -> head-win; else a tracked option wins.  head / dbp were taken during the preparation; both only
+        // shrink over time and a list exhausted since then ends below the head it had then, so:
+        //   best >= max(head, dbp)                      -> tracked win (nothing untracked can beat it)
+        //   head <= best < dbp                          -> dbound* >= dbp > best >= head*: the round ends
+        //   head > best, head's node still untracked    -> head* == head; dbound* > head* iff dbp > head
+        //   head > best, head's node tracked by now     -> re-validate the lists inside the ticket (exact) and apply the rule
+        // -- the same outcome whatever the timing of the preparation: replicated resolvers stay in lock step.
+        unsigned long long hd = head;
+        if ((hd > dbp ? hd : dbp) > best) {
+          if (hd <= best) reason = 3;
+          else if (!hset_has(S, key_node(hd))) { if (dbp > hd) reason = 3; }
+          else {
+            maintain_heads(S, lk, D, rke, s, lane, true);
+            hd = S.bh[s];
+            if (S.dbound[s] > (hd > best ? hd : best)) reason = 3;
+            PROF_C(15, 1)
+          }
+        }
+        const bool from_head = reason == 0 && hd > best;
+        const unsigned long long win = from_head ? hd : best;
         int nT = 0;
-        if (dry) reason = 3;
-        else if (from_head) { nT = S.nT; if (nT >= NT) reason = 2; }
+        if (from_head) { nT = S.nT; if (nT >= NT) reason = 2; }
 #ifdef EGS_RESOLVE_PROF
         long long q2_ = clock64() + (reason & 0) + ((int)win & 0);
         long long q3_ = q2_;

@@ -103,7 +103,10 @@ def test_sharded_engine_in_process_equals_unsharded(world):
     import egs_b200
     cap = egs_b200.capi
     F = ["node", "status", "alloc_mask", "fit_count", "fit_digest", "score_digest"]
-    cases = [(4, None, 30000, None), (1, None, None, None), (2, 3000, 6000, None), (3, 300, 2000, 0), (4, 1000, 3000, 0)]
+    # config 4 at full node count, long enough that nearly every round ends on a dry per-shard list (at 8 shards each
+    # contributes only 32 candidates per shape): the replicated resolvers must stop at the SAME pod on every rank
+    cases = [(4, None, 200000 if world == 8 else 60000, None), (1, None, None, None), (2, 3000, 6000, None), (3, 300, 2000, 0),
+             (4, 1000, 3000, 0)]
     for cfg, nn, npods, pol in cases:
         w = egs_b200.workloads.config(cfg, n_nodes=nn, n_pods=npods, policy=pol)
         e0 = egs_b200.Egs(w.policy, w.n_nodes)
