@@ -79,8 +79,22 @@ def build_devhost(force: bool = False) -> str:
     return LIBDEVHOST
 
 
+SHIM_DOUBLE = os.path.join(ROOT, "integration", "_build", "shim_double")
+
+
+def build_shim_double(force: bool = False) -> str:
+    """C test double of the Go shim (integration/shim_double.c): same libegs calls, same order."""
+    src = os.path.join(ROOT, "integration", "shim_double.c")
+    build_libegs(force)
+    if force or _stale(SHIM_DOUBLE, [src, LIBEGS, os.path.join(ROOT, "include", "egs.h")]):
+        os.makedirs(os.path.dirname(SHIM_DOUBLE), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-o", SHIM_DOUBLE, src, "-L" + LIBDIR, "-legs", "-Wl,-rpath," + LIBDIR])
+    return SHIM_DOUBLE
+
+
 def build_all(force: bool = False) -> None:
     build_synth(force)
     build_libegs(force)
     build_host(force)
     build_devhost(force)
+    build_shim_double(force)

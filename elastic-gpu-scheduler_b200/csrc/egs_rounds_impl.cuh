@@ -177,8 +177,7 @@ static int batch_rounds(egs_handle *h, int P, const int32_t *c_off, const egs_un
   MwConfig cfg = mw_config(ns_cfg);
   // sharded: every shard contributes its own list; the resolver holds about the same number of candidates per
   // shape in total, so each shard gathers (and ships) fewer
-  if (h->world > 4) cfg.rkm = std::min(cfg.rkm, 32);
-  else if (h->world > 2) cfg.rkm = std::min(cfg.rkm, 64);
+  if (h->world > 2) cfg.rkm = std::min(cfg.rkm, 64);          // (the resolver keeps what its shared memory holds: rke below)
   const BufLayout L = make_layout(ns_cfg, cfg.rkm);
   TRY(rounds_ensure(h, P, L));
 

@@ -11,17 +11,11 @@ from scenario import CBackend, make_scenario, run_scenario
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "integration", "shim_double.c")
-EXE = os.path.join(ROOT, "integration", "_build", "shim_double")
 
 
 def build_double() -> str:
     import egs_b200
-    lib = egs_b200._build.build_libegs()
-    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(SRC), os.path.getmtime(lib)):
-        os.makedirs(os.path.dirname(EXE), exist_ok=True)
-        subprocess.check_call(["gcc", "-O2", "-o", EXE, SRC, "-L" + os.path.dirname(lib), "-legs",
-                               "-Wl,-rpath," + os.path.dirname(lib)])
-    return EXE
+    return egs_b200._build.build_shim_double()
 
 
 def _req(shape):
