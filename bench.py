@@ -81,7 +81,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.rows, self.proc, self.gpu = [], None, gpu_index
+        self.rows, self.proc, self.gpu, self.t0 = [], None, gpu_index, 0.0
 
     def start(self):
         try:
@@ -93,7 +93,12 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.monotonic(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        """The timed region starts now: only samples taken from here on are reported.  (nvidia-smi is started before
+        the warm-up so that its start-up -- NVML initialisation takes driver locks -- does not land in a timed step.)"""
+        self.t0 = time.monotonic()
 
     def stop(self):
         if self.proc:
@@ -102,10 +107,11 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
-        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
-        mx = [int(float(r[2])) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if t >= self.t0] or [r for _, r in self.rows]
+        sm = sorted(int(float(r[1])) for r in rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
+        reasons = sorted({names[i] for r in rows if len(r) >= 8 for i in range(4) if r[4 + i].lower() == "active"})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm)}
 
@@ -343,12 +349,13 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)   # max over ranks
         return float(ms.item())
 
-    for _ in range(args.warmup):
-        step_resident()
-    e.profile_reset(False)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
+    for _ in range(args.warmup):
+        step_resident()
+    e.profile_reset(False)
+    clocks.mark()
     ms_total = timed(step_resident, args.steps)
     launches = sum(e.profile_get(k)[0] for k in range(8))
     ev_launches, ev_ms = e.profile_get(cap.EGS_K_EVALUATE)       # cold-shape table fills inside the timed steps

@@ -947,11 +947,15 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
         } else {
           for (int i = lane; i < a.L.cand_bytes / 16; i += 32) reinterpret_cast<int4 *>(dst)[i] = reinterpret_cast<const int4 *>(src)[i];
         }
+        __syncwarp();                                                     // every lane has compared hpay_node
         if (lane == 0) S.hpay_node[s] = (int)key_node(head);
         __syncwarp();
       }
-      const int pu = S.pu[s];
-      const bool fast = mono && S.rq_single[s] && pu != -2 && ld_vol(&S.n_observed) == ns;
+      // n_observed BEFORE pu: other warps write pu[s] / the aggregates of s (general_pod, inside their tickets) only while
+      // some shape of the round is unobserved; once n_observed == ns was seen, everything read below is owner-private
+      const int n_obs = ld_vol(&S.n_observed);
+      const int pu = ld_vol(&S.pu[s]);
+      const bool fast = mono && S.rq_single[s] && pu != -2 && n_obs == ns;
       // fast pods: the best tracked option of s over the slots seen so far, and everything the ticket will need
       unsigned long long pre_best = 0; int pre_t = -1;
       const int u = pu, uu = max(pu, 0);
