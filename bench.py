@@ -84,9 +84,11 @@ class ClockSampler:
         self.rows, self.proc, self.gpu, self.t0 = [], None, gpu_index, 0.0
 
     def start(self):
+        if os.environ.get("EGS_CLOCKS_LMS") == "0":     # diagnostic only: no sampler at all
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", os.environ.get("EGS_CLOCKS_LMS", "200"), "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
