@@ -24,12 +24,15 @@ struct NodeUidHash {
 };
 struct Shape { int C; egs_unit u[EGS_C]; };
 
+// Pinned host buffer holding (node[n], status[n]) of a batch.  Recycled through egs_handle::pin_pool: cudaMallocHost /
+// cudaFreeHost cost milliseconds and synchronise the device -- too much for a small batch on the extender's path.
+struct PinBuf { int32_t *p = nullptr; size_t cap = 0; };   // cap in int32 elements
 struct PendingBatch {           // results of a batch whose uid bookkeeping is applied lazily
-  int n; uint64_t uid0; std::vector<uint64_t> uids; int32_t *h_node, *h_status; cudaEvent_t done;
+  int n; uint64_t uid0; std::vector<uint64_t> uids; int32_t *h_node, *h_status; PinBuf buf; cudaEvent_t done;
 };
 // A finished batch with library-assigned UIDs [uid0, uid0+n): podsMap / podMaps membership is read
 // straight from the result arrays (node.go:150, scheduler.go:224) -- no per-pod hash insert.
-struct AutoBatch { uint64_t uid0; int n; int32_t *h_node, *h_status; bool nodes_valid; };
+struct AutoBatch { uint64_t uid0; int n; int32_t *h_node, *h_status; PinBuf buf; bool nodes_valid; };
 
 struct egs_handle {
   int policy = 0, max_nodes = 0, n_pad = 0, g_max = 0, device = 0;
@@ -52,6 +55,7 @@ struct egs_handle {
   std::unordered_set<uint64_t> pod_maps, released;             // BaseScheduler.podMaps / releasedPodMap
   std::vector<PendingBatch> pending;
   std::vector<AutoBatch> auto_batches;
+  std::vector<PinBuf> pin_pool;                                 // idle pinned result buffers (at most PIN_POOL_MAX)
   std::unordered_set<uint64_t> auto_gone_pod;                  // auto uids erased from podMaps (ForgetPod)
   std::unordered_set<NodeUid, NodeUidHash> auto_gone_node;     // auto (node, uid) erased from a podsMap
   uint64_t next_uid = 0x8000000000000000ull;
@@ -215,8 +219,14 @@ static bool in_pod_maps(const egs_handle *h, uint64_t uid) {
   const AutoBatch *b = auto_find(h, uid);
   return b && b->h_node[uid - b->uid0] >= 0 && b->h_status[uid - b->uid0] == EGS_OK && !h->auto_gone_pod.count(uid);
 }
+constexpr size_t PIN_POOL_MAX = 4;
+static int pin_get(egs_handle *h, size_t n, PinBuf *out);
+static void pin_put(egs_handle *h, PinBuf b) {
+  if (!b.p) return;
+  if (h->pin_pool.size() < PIN_POOL_MAX) h->pin_pool.push_back(b); else cudaFreeHost(b.p);
+}
 static void free_auto_batches(egs_handle *h) {
-  for (auto &b : h->auto_batches) { cudaFreeHost(b.h_node); cudaFreeHost(b.h_status); }
+  for (auto &b : h->auto_batches) pin_put(h, b.buf);
   h->auto_batches.clear(); h->auto_gone_pod.clear(); h->auto_gone_node.clear();
 }
 
@@ -224,7 +234,7 @@ static int flush_pending(egs_handle *h) {
   for (auto &b : h->pending) {
     CK(h, cudaEventSynchronize(b.done));
     if (b.uids.empty()) {                                        // library-assigned contiguous uids: keep the arrays
-      h->auto_batches.push_back(AutoBatch{b.uid0, b.n, b.h_node, b.h_status, true});
+      h->auto_batches.push_back(AutoBatch{b.uid0, b.n, b.h_node, b.h_status, b.buf, true});
       cudaEventDestroy(b.done);
       continue;
     }
@@ -235,7 +245,7 @@ static int flush_pending(egs_handle *h) {
         if (b.h_status[p] == EGS_OK) h->pod_maps.insert(uid);          // scheduler.go:224
       }
     }
-    cudaFreeHost(b.h_node); cudaFreeHost(b.h_status); cudaEventDestroy(b.done);
+    pin_put(h, b.buf); cudaEventDestroy(b.done);
   }
   h->pending.clear();
   return EGS_OK;
@@ -245,6 +255,17 @@ struct Guard {
   egs_handle *h; std::lock_guard<std::mutex> lk;
   explicit Guard(egs_handle *hh) : h(hh), lk(hh->mu) { cudaSetDevice(hh->device); }
 };
+
+static int pin_get(egs_handle *h, size_t n, PinBuf *out) {
+  int best = -1;                                                // smallest idle buffer that is large enough
+  for (size_t i = 0; i < h->pin_pool.size(); i++)
+    if (h->pin_pool[i].cap >= n && (best < 0 || h->pin_pool[i].cap < h->pin_pool[(size_t)best].cap)) best = (int)i;
+  if (best >= 0) { *out = h->pin_pool[(size_t)best]; h->pin_pool.erase(h->pin_pool.begin() + best); return EGS_OK; }
+  PinBuf b; b.cap = std::max(n, (size_t)4096);
+  CK(h, cudaMallocHost(&b.p, b.cap * sizeof(int32_t)));
+  *out = b;
+  return EGS_OK;
+}
 
 // ------------------------------------------------------------------------------- lifecycle
 extern "C" int egs_create(int policy, int max_nodes, int g_max, int device, egs_handle **out) {
@@ -291,6 +312,8 @@ extern "C" int egs_destroy(egs_handle *h) {
   cudaStreamSynchronize(h->stream);
   flush_pending(h);
   free_auto_batches(h);
+  for (auto &b : h->pin_pool) cudaFreeHost(b.p);
+  h->pin_pool.clear();
   rounds_free(&h->rounds);
   void *dev[] = {h->d_core, h->d_mem, h->d_mem_total, h->d_st, h->d_sc, h->d_al, h->d_partials, h->d_ticket, h->d_snap_core, h->d_snap_mem, h->d_snap_total,
                  h->d_result, h->d_ids, h->d_fit, h->d_score, h->d_ev_fit, h->d_ev_score, h->d_ev_gpu, h->d_flush,
@@ -404,7 +427,7 @@ static void drop_node_pods(egs_handle *h, int node0, int n) {
 static int discard_pending(egs_handle *h) {
   for (auto &b : h->pending) {
     CK(h, cudaEventSynchronize(b.done));
-    cudaFreeHost(b.h_node); cudaFreeHost(b.h_status); cudaEventDestroy(b.done);
+    pin_put(h, b.buf); cudaEventDestroy(b.done);
   }
   h->pending.clear();
   return EGS_OK;
@@ -651,7 +674,7 @@ static int apply_lists(egs_handle *h, int cancel, int node_id, int C, const egs_
   a.all_st = h->d_st; a.slot_stride = (size_t)h->n_pad; a.n_slots = (int)h->shapes.size();
   for (int c = 0; c < C; c++) {
     int n = alloc_off ? alloc_off[c + 1] - alloc_off[c] : 0;
-    if (n < 0 || n > EGS_G) return EGS_ERR_BAD_ARG;
+    if (n < 0 || n > EGS_G || (n > 0 && !alloc_idx)) return EGS_ERR_BAD_ARG;
     a.n_idx[c] = n;
     for (int j = 0; j < n; j++) {
       int v = alloc_idx[alloc_off[c] + j];
@@ -897,8 +920,8 @@ static int batch_common(egs_handle *h, int mode, int P, const int32_t *c_off, co
   if (n_done > 0) {
     PendingBatch pb; pb.n = n_done; pb.uid0 = h->next_uid;
     if (uids) pb.uids.assign(uids, uids + n_done); else h->next_uid += (uint64_t)n_done;
-    CK(h, cudaMallocHost(&pb.h_node, sizeof(int32_t) * (size_t)n_done));
-    CK(h, cudaMallocHost(&pb.h_status, sizeof(int32_t) * (size_t)n_done));
+    TRY(pin_get(h, 2 * (size_t)n_done, &pb.buf));
+    pb.h_node = pb.buf.p; pb.h_status = pb.buf.p + n_done;
     CK(h, cudaMemcpyAsync(pb.h_node, dev.node, sizeof(int32_t) * (size_t)n_done, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaMemcpyAsync(pb.h_status, dev.status, sizeof(int32_t) * (size_t)n_done, cudaMemcpyDeviceToHost, h->stream));
     CK(h, cudaEventCreateWithFlags(&pb.done, cudaEventDisableTiming));

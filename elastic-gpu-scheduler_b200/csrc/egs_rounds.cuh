@@ -865,7 +865,7 @@ __global__ void __launch_bounds__(32 * MW_MAX_WARPS, 1) k_resolve_mw(MwArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SM = MwSmem<NS, NT>;
   SM &S = *reinterpret_cast<SM *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthreads = blockDim.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = a.n_shards, rke = a.rke, nw = a.nw;
   const int ns = a.rd->ns;
   unsigned long long *lk = reinterpret_cast<unsigned long long *>(smem_raw + ((sizeof(SM) + 15) & ~(size_t)15));   // [ns][D][rke]
