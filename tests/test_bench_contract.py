@@ -27,3 +27,17 @@ def test_ncu_traffic_summary_is_readable():
     bench = importlib.import_module("bench")
     t, src = bench.ncu_traffic()
     assert t is None or (t > 2.0e8 and t < 3.2e8), (t, src)   # ~276 MB per 4M-node launch vs 280 MB algorithmic
+
+
+def test_reference_arm_under_torchrun_prints_once():
+    """The driver launches the reference arm like the GPU arm (torchrun, N ranks): rank 0 alone measures and prints,
+    the other ranks exit 0 without work."""
+    port = 29900 + os.getpid() % 500
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--cfg", "1", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [json.loads(x) for x in r.stdout.splitlines() if x.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    assert lines[0]["impl"] == "reference" and lines[0]["n_gpus"] == 2 and lines[0]["value"] > 0
