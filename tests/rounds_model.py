@@ -1,10 +1,12 @@
 """Executable model of EGS_MODE_ROUNDS (csrc/egs_rounds.cuh) in plain Python.
 
-It follows the device algorithm step for step -- option states ABSENT/CACHED/UNFIT/NEW, `k_select`
-evaluating absent options ahead of time, top-K candidate lists per (shard, shape), the sequential
-resolver with its tracked-node table, pending re-evaluation, invalidation rules, the monotone
-shortcut, sticky observation flags and the end-of-batch finalize -- but with K, T, RS as parameters so
-tests can force every early-termination path.  Trade / Transact come from the python mirror of the
+It follows the device algorithm's SERIAL semantics step for step -- option states ABSENT/CACHED/UNFIT/NEW,
+`k_select` evaluating absent options ahead of time, top-K candidate lists per (shard, shape), the resolver's
+tracked-node table, pending re-evaluation, invalidation rules, the monotone shortcut, the fast pod / general pod
+split with their different stop conditions, the exact "list ran dry" rule (dbound), sticky observation flags and
+the end-of-batch finalize -- but with K, T, RS as parameters so tests can force every early-termination path.
+(What the model leaves out is WHO computes what when: the owner warps' lazy list maintenance and speculative
+Trades.  That those cannot change a decision is the subject of tests/test_resolver_rule.py.)  Trade / Transact come from the python mirror of the
 reference (oracle/egs_oracle.py), so the model checks the ROUND STRUCTURE, not the arithmetic.
 """
 from __future__ import annotations
@@ -33,12 +35,12 @@ class Entry:
 
 
 class RoundsModel:
-    def __init__(self, policy: int, K: int = 32, T: int = 256, RS: int = 32, shards: int = 1, window: int = 1):
-        self.policy, self.K, self.T, self.RS, self.D, self.W = policy, K, T, RS, shards, window
+    def __init__(self, policy: int, K: int = 32, T: int = 256, RS: int = 32, shards: int = 1):
+        self.policy, self.K, self.T, self.RS, self.D = policy, K, T, RS, shards
         self.nodes: List[List[po.GPU]] = []
         self.tables: Dict[tuple, List[Entry]] = {}          # shape -> per-node entries
         self.obs_pending: Dict[tuple, bool] = {}
-        self.stats = dict(rounds=0, dry=0, full=0, shape=0, windows=0, window_pods=0, cuts=0)
+        self.stats = dict(rounds=0, dry=0, dry_harmless=0, full=0, shape=0, fast=0)
 
     # ---- state
     def add_node(self, core_alloc: int, mem_alloc: int) -> int:
@@ -124,88 +126,21 @@ class RoundsModel:
             done = 0
             p = p0
             while p < plim:
-                # ---- 4-wide window (device fast path): mono round, every shape observed, distinct shapes,
-                # <= 1 pending option per shape, room in the tracked table.  Decisions are taken from the SAME
-                # state, then cut at the first hazard, then committed in order WITHOUT being recomputed.
-                if self.W > 1 and mono and all(observed.values()) and len(tracked) + self.W <= self.T:
-                    win_shapes = []
-                    for q in range(self.W):
-                        if p + q >= plim or pods[p + q] in win_shapes or pods[p + q] not in lists:
-                            break
-                        win_shapes.append(pods[p + q])
-                    decs = []
-                    for s in win_shapes:
-                        pend = [n_ for n_, ent in tracked.items() if ent[s][0] == ABSENT]
-                        heads, dry = [], False
-                        for d in range(self.D):
-                            keys, more = lists[s][d]
-                            c = cur[s][d]
-                            while c < len(keys) and keys[c][1] in tracked:
-                                c += 1
-                            if c < len(keys):
-                                heads.append(keys[c])
-                            elif more:
-                                dry = True
-                        if len(pend) > 1 or dry:
-                            break
-                        u = pend[0] if pend else None
-                        topt = self._trade(rows_copy[u], s) if u is not None else None
-                        cands = [(-ent[s][1], n_) for n_, ent in tracked.items() if ent[s][0] in (CACHED, NEW)] + heads
-                        if topt is not None:
-                            cands.append((-topt.score, u))
-                        fitc, ofd, osd = agg[s]
-                        if topt is not None:
-                            fitc, ofd, osd = fitc + 1, (ofd + fit_term(u)) & MASK64, (osd + score_term(u, topt.score)) & MASK64
-                        w = min(cands)[1] if cands else None
-                        decs.append(dict(s=s, u=u, topt=topt, w=w, head=(w is not None and w not in tracked), agg=(fitc, ofd, osd)))
-                    nW = len(decs)
-                    for j in range(1, nW):                        # hazards
-                        if any((decs[i]["head"] and not getattr(self, "relax_head", False)) or
-                               (decs[j]["u"] is not None and decs[j]["u"] == decs[i]["w"] and not decs[i]["head"]) for i in range(j)):
-                            nW = j
-                            self.stats["cuts"] += 1
-                            break
-                    if nW >= 2:
-                        self.stats["windows"] += 1
-                        self.stats["window_pods"] += nW
-                        for dec in decs[:nW]:
-                            s, u, topt, w = dec["s"], dec["u"], dec["topt"], dec["w"]
-                            fitc, ofd, osd = dec["agg"]
-                            if u is not None:                     # the Trade result of this pod's filter
-                                e = tracked[u][s]
-                                if topt is None:
-                                    e[0] = UNFIT
-                                else:
-                                    e[0], e[1], e[2] = CACHED, topt.score, topt.allocated
-                            agg[s] = [fitc, ofd, osd]
-                            if w is None:
-                                out.append(dict(node=-1, status=po.EGS_ERR_NOFIT, alloc=None, fit_count=fitc, fit_digest=ofd, score_digest=osd))
-                            else:
-                                if w not in tracked:
-                                    rows_copy[w] = self.nodes[w]
-                                    tracked[w] = {s2: [CACHED if (self.tables[s2][w].st == NEW) else self.tables[s2][w].st,
-                                                       self.tables[s2][w].score, self.tables[s2][w].alloc] for s2 in shapes}
-                                e = tracked[w][s]
-                                opt = po.GPUOption(request=list(s), allocated=e[2], score=e[1])
-                                e[0] = ABSENT
-                                agg[s] = [fitc - 1, (ofd - fit_term(w)) & MASK64, (osd - score_term(w, e[1])) & MASK64]
-                                ok = po.transact(rows_copy[w], opt)
-                                dirty.add(w)
-                                out.append(dict(node=w, status=po.EGS_OK if ok else po.EGS_ERR_TRANSACT, alloc=opt.allocated if ok else None,
-                                                fit_count=fitc, fit_digest=ofd, score_digest=osd))
-                            p += 1
-                            done += 1
-                        continue
                 s = pods[p]
                 if s not in lists:
                     self.stats["shape"] += 1
                     break
-                if len(tracked) >= self.T:
+                pend = [n_ for n_, ent in tracked.items() if ent[s][0] == ABSENT]
+                # device: k_resolve_mw's fast pod -- monotone round, single fractional container, every shape of the
+                # round observed, at most one pending option (pu != -2); everything else goes through general_pod
+                fast = (mono and len(s) == 1 and s[0][2] == 0 and s[0][0] >= 0 and s[0][1] >= 0
+                        and all(observed.values()) and len(pend) <= 1)
+                if not fast and len(tracked) >= self.T:           # general_pod: no free slot for a possible new winner
                     self.stats["full"] += 1
                     break
-                # heads (skip candidates that became tracked)
-                heads = []
-                dry = False
+                # exact heads of the untracked candidate lists (entries that became tracked are skipped) and dbound =
+                # the best last key of an exhausted TRUNCATED list: what such a list did not show is worse than that
+                heads, dbound = [], None
                 for d in range(self.D):
                     keys, more = lists[s][d]
                     c = cur[s][d]
@@ -214,21 +149,21 @@ class RoundsModel:
                     cur[s][d] = c
                     if c < len(keys):
                         heads.append(keys[c])
-                    elif more:
-                        dry = True
-                if dry:
-                    self.stats["dry"] += 1
-                    break
-                if not observed[s]:
+                    elif more and keys:
+                        dbound = keys[-1] if dbound is None else min(dbound, keys[-1])
+                if not fast and not observed[s]:
                     for n_, ent in tracked.items():
                         if ent[s][0] == NEW:
                             ent[s][0] = CACHED
                     observed[s] = True
-                # tracked nodes: Trade absent options now
-                for n_, ent in tracked.items():
-                    e = ent[s]
-                    if e[0] == ABSENT:
-                        opt = self._trade(rows_copy[n_], s)
+                # this pod's filter Trades the absent options of tracked nodes.  general_pod records the results before
+                # it decides whether the round goes on (the next round's first filter would do the same Trades on the
+                # same rows); the fast pod Trades speculatively and records after the decision.
+                traded = [(n_, self._trade(rows_copy[n_], s)) for n_ in pend]
+
+                def record():
+                    for n_, opt in traded:
+                        e = tracked[n_][s]
                         if opt is None:
                             e[0] = UNFIT
                         else:
@@ -236,14 +171,32 @@ class RoundsModel:
                             agg[s][0] += 1
                             agg[s][1] = (agg[s][1] + fit_term(n_)) & MASK64
                             agg[s][2] = (agg[s][2] + score_term(n_, opt.score)) & MASK64
-                cands = [(-ent[s][1], n_) for n_, ent in tracked.items() if ent[s][0] in (CACHED, NEW)] + heads
+                if not fast:
+                    record()
+                    traded_c = []
+                else:
+                    traded_c = [(-opt.score, n_) for n_, opt in traded if opt is not None]
+                cands = [(-ent[s][1], n_) for n_, ent in tracked.items() if ent[s][0] in (CACHED, NEW)] + traded_c + heads
+                win = min(cands) if cands else None
+                # the exact stop rule: a truncated list ran dry AND what it hides could beat the winner
+                if dbound is not None:
+                    if win is None or dbound < win:
+                        self.stats["dry"] += 1
+                        break
+                    self.stats["dry_harmless"] += 1
+                if win is not None and win[1] not in tracked and len(tracked) >= self.T:   # (fast pods only get here)
+                    self.stats["full"] += 1
+                    break
+                if fast:
+                    record()
+                    self.stats["fast"] += 1
                 fitc, ofd, osd = agg[s]
-                if not cands:
+                if win is None:
                     out.append(dict(node=-1, status=po.EGS_ERR_NOFIT, alloc=None, fit_count=fitc, fit_digest=ofd, score_digest=osd))
                     p += 1
                     done += 1
                     continue
-                negs, w = min(cands)
+                w = win[1]
                 if w not in tracked:                              # head-win: the node becomes tracked
                     rows_copy[w] = self.nodes[w]                  # (the model mutates the node rows in place)
                     ent = {}

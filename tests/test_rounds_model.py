@@ -76,7 +76,7 @@ def test_model_equals_oracle(seed):
 
 
 def test_early_termination_paths_are_exercised():
-    tot = dict(rounds=0, dry=0, full=0, shape=0)
+    tot = dict(rounds=0, dry=0, dry_harmless=0, full=0, shape=0, fast=0)
     for seed in range(24):
         rng = np.random.default_rng(seed)
         K, T, RS, D = int(rng.choice([1, 2, 3, 8])), int(rng.choice([2, 3, 5, 64])), int(rng.choice([1, 2, 4, 32])), int(rng.choice([1, 2, 3]))
@@ -90,71 +90,52 @@ def test_early_termination_paths_are_exercised():
         m.schedule_batch([shapes[int(i)] for i in rng.integers(0, len(shapes), 150)])
         for k in tot:
             tot[k] += m.stats[k]
-    assert tot["dry"] > 0 and tot["full"] > 0 and tot["shape"] > 0, tot
+    assert tot["dry"] > 0 and tot["dry_harmless"] > 0 and tot["full"] > 0 and tot["shape"] > 0 and tot["fast"] > 0, tot
 
 
-@pytest.mark.parametrize("seed", range(30))
-def test_windowed_decisions_with_hazard_cut_are_exact(seed):
-    """The 4-wide window of k_resolve: decisions taken from one state + the hazard rule == sequential."""
-    rng = np.random.default_rng(1000 + seed)
+def _fast_regime(seed):
+    rng = np.random.default_rng(5000 + seed)
+    K, T, D = int(rng.choice([1, 2, 4])), int(rng.choice([2, 3, 4, 6])), int(rng.choice([1, 2, 3]))
+    nodes = _cluster(rng, int(rng.integers(6, 30)))
+    shapes = [((int(rng.choice([5, 10, 25, 50])), int(rng.integers(1, 12)), 0),) for _ in range(int(rng.integers(1, 5)))]
+    pods = [shapes[int(i)] for i in rng.integers(0, len(shapes), 200)]
+    return K, T, D, nodes, pods
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fast_pods_full_table_and_dry_lists_stay_exact(seed):
+    """Monotone rounds of single-container shapes (the benchmark regime): fast pods go on resolving on a FULL tracked
+    table as long as tracked options win, and an exhausted truncated list ends the round only when what it hides could
+    beat the winner -- output for output the oracle's."""
     policy = seed % 2
-    n_nodes = int(rng.integers(2, 12))                            # tiny clusters: shapes collide on nodes all the time
-    nodes = _cluster(rng, n_nodes)
-    shapes = [tuple([(int(rng.choice([0, 5, 10, 25, 50])), int(rng.integers(1, 12)), 0)]) for _ in range(int(rng.integers(2, 9)))]
+    K, T, D, nodes, pods = _fast_regime(seed)
     o = po.Scheduler(policy)
-    m = RoundsModel(policy, K=int(rng.choice([2, 4, 32])), T=int(rng.choice([8, 64])), RS=32, shards=int(rng.choice([1, 2])), window=4)
+    m = RoundsModel(policy, K=K, T=T, RS=8, shards=D)
     for core, mem, rows in nodes:
         a = o.add_node(core, mem); m.add_node(core, mem)
         if rows:
             o.set_rows(a, *rows); m.set_rows(a, *rows)
-    uid = 0
-    for batch in range(2):
-        pods = [shapes[int(i)] for i in rng.integers(0, len(shapes), 300)]
-        got = m.schedule_batch(pods)
-        for p, (s, g) in enumerate(zip(pods, got)):
-            r = o.schedule_one(list(s), uid); uid += 1
-            assert g == dict(node=r["node"], status=r["status"], alloc=r["alloc"], fit_count=r["fit_count"],
-                             fit_digest=r["fit_digest"], score_digest=r["score_digest"]), (seed, batch, p)
-        for n in range(n_nodes):
-            assert m.rows(n) == o.rows(n)
-    assert m.stats["windows"] > 0
+    got = m.schedule_batch(pods)
+    for p, (s, g) in enumerate(zip(pods, got)):
+        r = o.schedule_one(list(s), p)
+        want = dict(node=r["node"], status=r["status"], alloc=r["alloc"], fit_count=r["fit_count"],
+                    fit_digest=r["fit_digest"], score_digest=r["score_digest"])
+        assert g == want, (seed, p, K, T, D)
+    for n in range(len(nodes)):
+        assert m.rows(n) == o.rows(n)
+    assert m.stats["fast"] > 0
 
 
-def test_windows_and_cuts_happen():
-    tot = dict(windows=0, window_pods=0, cuts=0)
-    for seed in range(30):
-        rng = np.random.default_rng(1000 + seed)
-        nodes = _cluster(rng, int(rng.integers(2, 12)))
-        shapes = [tuple([(int(rng.choice([0, 5, 10, 25, 50])), int(rng.integers(1, 12)), 0)]) for _ in range(int(rng.integers(2, 9)))]
-        m = RoundsModel(seed % 2, K=4, T=64, RS=32, shards=1, window=4)
+def test_fast_regime_paths_are_exercised():
+    tot = dict(dry=0, dry_harmless=0, full=0, fast=0)
+    for seed in range(16):
+        K, T, D, nodes, pods = _fast_regime(seed)
+        m = RoundsModel(seed % 2, K=K, T=T, RS=8, shards=D)
         for core, mem, rows in nodes:
             a = m.add_node(core, mem)
             if rows:
                 m.set_rows(a, *rows)
-        m.schedule_batch([shapes[int(i)] for i in rng.integers(0, len(shapes), 300)])
+        m.schedule_batch(pods)
         for k in tot:
             tot[k] += m.stats[k]
-    assert tot["windows"] > 100 and tot["cuts"] > 20 and tot["window_pods"] > 2 * tot["windows"], tot
-
-
-@pytest.mark.parametrize("seed", range(12))
-def test_relaxed_head_cut_and_wider_windows_stay_exact(seed):
-    """Round-2 candidate: no cut after a head-win (a second pick of the same node is a tracked win) and 8-wide windows."""
-    rng = np.random.default_rng(2000 + seed)
-    policy = seed % 2
-    nodes = _cluster(rng, int(rng.integers(2, 14)))
-    shapes = [tuple([(int(rng.choice([0, 5, 10, 25, 50])), int(rng.integers(1, 12)), 0)]) for _ in range(int(rng.integers(3, 12)))]
-    o = po.Scheduler(policy)
-    m = RoundsModel(policy, K=int(rng.choice([2, 4, 32])), T=64, RS=32, shards=int(rng.choice([1, 2])), window=8)
-    m.relax_head = True
-    for core, mem, rows in nodes:
-        a = o.add_node(core, mem); m.add_node(core, mem)
-        if rows:
-            o.set_rows(a, *rows); m.set_rows(a, *rows)
-    pods = [shapes[int(i)] for i in rng.integers(0, len(shapes), 400)]
-    got = m.schedule_batch(pods)
-    for uid, (s, g) in enumerate(zip(pods, got)):
-        r = o.schedule_one(list(s), uid)
-        assert g == dict(node=r["node"], status=r["status"], alloc=r["alloc"], fit_count=r["fit_count"],
-                         fit_digest=r["fit_digest"], score_digest=r["score_digest"]), (seed, uid)
-    assert m.stats["windows"] > 0
+    assert all(v > 0 for v in tot.values()), tot
