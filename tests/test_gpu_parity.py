@@ -91,7 +91,7 @@ def test_cfg1_full(mode):
 @pytest.mark.parametrize("mode", [1, 2])
 def test_cfg2_prefix(mode):
     """config 2 (spread, core+memory): 10000 nodes, first 20000 pods against the oracle."""
-    _compare_batch(_egs().workloads.config(2, n_pods=20000), mode)
+    _compare_batch(_egs().workloads.config(2, n_pods=20000), mode, threads=4)
 
 
 @pytest.mark.parametrize("policy", [1, 0])
