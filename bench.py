@@ -464,6 +464,17 @@ def main():
                 "at_workload_n": {"nodes": w.n_nodes, "l2_hot_GBps": w.n_nodes * b_eval / (ms_hot * 1e-3) / 1e9,
                                   "l2_flushed_GBps": w.n_nodes * b_eval / (ms_cold * 1e-3) / 1e9,
                                   "ms_hot": ms_hot, "ms_flushed": ms_cold}}
+        try:
+            # the literal design of the driver rule -- one full pass over the node rows per pod -- is HBM-bound at
+            # peak / (N * bytes per node) decisions/s per GPU; the rounds engine does not re-read the rows per pod
+            per_pod = float(w.n_nodes * b_eval)
+            cap = world * peak * 1e9 / per_pod
+            roof["per_pod_rescan"] = {"bytes_per_decision": per_pod, "hbm_roofline_decisions_per_s": cap,
+                                      "value_over_that_roofline": value / cap,
+                                      "note": "ceiling of ANY implementation that streams the node rows once per pod, at the "
+                                              "measured HBM peak on all GPUs of the run; `value` is measured against it"}
+        except Exception:  # never let a derived figure break the bench line
+            pass
 
     cpu = None
     if not args.no_cpu:
