@@ -42,6 +42,21 @@ def build_libegs(force: bool = False, verbose: bool = False) -> str:
     return LIBEGS
 
 
+LIBPROF = os.path.join(LIBDIR, "libegs_prof.so")
+
+
+def build_prof(force: bool = False) -> str:
+    """PROFILING ONLY (tools/gpu_round.sh, tools/prof_sections.py with EGS_LIB=libegs_prof.so): libegs with the
+    resolver's clock64 section counters compiled in (-DEGS_RESOLVE_PROF).  Not part of build_all."""
+    srcs = sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cuh")) +
+                  [os.path.join(ROOT, "include", "egs.h")])
+    if force or _stale(LIBPROF, srcs):
+        os.makedirs(LIBDIR, exist_ok=True)
+        flags = [f for f in NVCC_FLAGS if f != "-DEGS_RESOLVE_PROF"]
+        subprocess.check_call([nvcc_path(), "-DEGS_RESOLVE_PROF"] + flags + ["-o", LIBPROF, os.path.join(CSRC, "egs_api.cu"), "-ldl"])
+    return LIBPROF
+
+
 def build_synth(force: bool = False) -> str:
     src = os.path.join(CSRC, "egs_synth.c")
     if force or _stale(LIBSYNTH, [src]):
