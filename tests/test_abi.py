@@ -76,3 +76,26 @@ def test_workload_generators():
     # prefix stability
     w2 = egs_b200.workloads.config(4, n_nodes=100, n_pods=50)
     assert (w2.core == w.core[:100]).all() and (w2.units == w.units[:50]).all()
+
+
+def test_mutation_record_layout_matches_the_c_struct(egs, tmp_path):
+    """capi.MUTATION_DTYPE (numpy) must be egs_mutation (include/egs.h) byte for byte: size and every field offset,
+    taken from a C program compiled against the header."""
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "egs.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %d %d\\n", sizeof(egs_mutation),'
+                   'offsetof(egs_mutation,kind),offsetof(egs_mutation,node_id),offsetof(egs_mutation,n_containers),'
+                   'offsetof(egs_mutation,units),offsetof(egs_mutation,n_idx),offsetof(egs_mutation,idx),'
+                   'offsetof(egs_mutation,uid),sizeof(egs_unit),EGS_MAX_CONTAINERS_APPLY,EGS_MAX_GPUS);return 0;}\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    v = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    dt = egs.MUTATION_DTYPE
+    assert v[0] == dt.itemsize
+    for off, name in zip(v[1:8], ["kind", "node_id", "n_containers", "units", "n_idx", "idx", "uid"]):
+        assert dt.fields[name][1] == off, name
+    assert v[8] == 12 and v[9] == egs.EGS_MAX_CONTAINERS_APPLY == 8 and v[10] == 8
+    a = egs.mutations_array([(egs.EGS_MUT_ADD, 7, [(10, 4096, 0), (-1, -1, 0)], [[3], []], 99)])
+    assert a[0]["node_id"] == 7 and a[0]["n_containers"] == 2 and a[0]["uid"] == 99
+    assert a[0]["units"][1].tolist() == [-1, -1, 0] and a[0]["n_idx"][:2].tolist() == [1, 0] and a[0]["idx"][0][0] == 3
